@@ -1,0 +1,175 @@
+"""TEST INFRASTRUCTURE — generate ``tests/golden/*.npz`` by running the UNMODIFIED reference.
+
+Run inside the build container (where ``/root/reference`` is mounted)::
+
+    python -m oracle.gen_golden
+
+The reference ships no tests or golden vectors, so parity is pinned on outputs
+of the reference's own functions executed here through ``oracle/ref_shim.py``.  Intermediate
+values that the reference keeps in local variables (``sim_sharp``, ``eff_edge_floor``,
+``W_all``, ``adj_sims``, the C99 rank matrix ...) are captured with ``sys.setprofile`` at the
+moment the reference function returns — the reference source is not edited or copied.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+
+from . import ref_shim
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def capture_locals(func, names, target_code_names, *args, **kwargs):
+    """Call ``func`` and return (result, {code_name: {local_name: value}}) captured at return."""
+    grabbed = {}
+
+    def prof(frame, event, _arg):
+        if event == "return" and frame.f_code.co_name in target_code_names:
+            loc = frame.f_locals
+            d = grabbed.setdefault(frame.f_code.co_name, {})
+            for nm in names:
+                if nm in loc:
+                    d[nm] = loc[nm]
+        return prof
+
+    sys.setprofile(prof)
+    try:
+        res = func(*args, **kwargs)
+    finally:
+        sys.setprofile(None)
+    return res, grabbed
+
+
+def topic_doc(rng, n, d, sent_per_topic=12, noise=0.7):
+    """SURVEY.md §8(d) config-2 generator: topic centroid + noise rows."""
+    n_topics = max(1, int(np.ceil(n / sent_per_topic)))
+    cent = rng.standard_normal((n_topics, d)).astype(np.float32)
+    topic_of = np.minimum(np.arange(n) // sent_per_topic, n_topics - 1)
+    return (cent[topic_of] + noise * rng.standard_normal((n, d)).astype(np.float32)).astype(np.float32)
+
+
+def gen_rank(ref):
+    rng = np.random.default_rng(101)
+    N, d, B = 257, 48, 6
+    C = rng.standard_normal((N, d)).astype(np.float32)
+    Q = rng.standard_normal((B, d)).astype(np.float32)
+    C[17] = 0.0                      # zero row -> similarity 0 (sklearn zero rule)
+    C[40] = C[3]                     # exact duplicate -> tie
+    C[41] = 2.5 * C[3]               # scaled duplicate -> tie up to rounding
+    Q[5] = C[3] * 0.5                # a query collinear with the duplicates
+    # (1) the exact expression at rank_chunks_optimized.py:215-216, one call per query
+    scores = np.stack([ref.rank.cosine_similarity(Q[b].reshape(1, -1), C)[0] for b in range(B)])
+    order = np.stack([np.argsort(-scores[b]) for b in range(B)])  # :225 (non-stable)
+    # (2) through OptimizedRanker.rank_single_query_optimized (rank:201-250)
+    texts = [f"chunk {i:04d}" for i in range(N)]
+    ref_shim.set_embeddings(texts + ["the query"], np.vstack([C, Q[0:1]]))
+    ranker = ref.rank.OptimizedRanker(model_name="m", device_preference="cpu", cache_size=100000)
+    df = pd.DataFrame({"chunk_id": [f"c{i}" for i in range(N)], "chunk_text": texts})
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ranked = ranker.rank_single_query_optimized("the query", df)
+    by_id = ranked.set_index("chunk_id").loc[df["chunk_id"]]
+    np.savez_compressed(
+        os.path.join(OUT_DIR, "rank_cosine.npz"), C=C, Q=Q, scores=scores.astype(np.float32),
+        order=order.astype(np.int64),
+        ranker_cosine_q0=by_id["cosine_score"].to_numpy(dtype=np.float32),
+        ranker_rrf_q0=by_id["rrf_score"].to_numpy(dtype=np.float64),
+        ranker_sorted_ids=np.array(ranked["chunk_id"].tolist()))
+
+
+def gen_simmatrix_and_grouping(ref):
+    rng = np.random.default_rng(202)
+    docs = {}
+    for name, n, d in (("a", 23, 40), ("b", 64, 32), ("c", 131, 24), ("tiny", 2, 16), ("seven", 7, 16)):
+        E = topic_doc(rng, n, d)
+        if name == "a":
+            E[5] = 0.0               # zero sentence vector -> zero row/col incl. diagonal
+        docs[name] = E
+    payload = {}
+    meta = {}
+    for name, E in docs.items():
+        text, sents = ref_shim.make_doc(E, tag=name)
+        S = ref.common.create_similarity_matrix(sents, "m", batch_size=64, device="cpu", silent=True)
+        payload[f"{name}_E"] = E
+        payload[f"{name}_S"] = S
+        stats = ref.common.analyze_similarity_distribution(S)
+        meta[f"{name}_dist"] = stats
+        names = ("sim_sharp", "centrality", "eff_edge_floor", "W_all", "k_eff_all", "eff_tau_merge",
+                 "eff_reassign_delta", "global_merge_thr", "merged", "method_used", "mu", "sigma")
+        out, grabbed = capture_locals(
+            ref.group.semantic_grouping_main, names, {"semantic_grouping_main"},
+            text, f"doc_{name}", "m", device="cpu", silent=True, collect_metadata=True)
+        loc = grabbed.get("semantic_grouping_main", {})
+        if "sim_sharp" in loc:
+            payload[f"{name}_sim_sharp"] = np.asarray(loc["sim_sharp"])
+            payload[f"{name}_centrality"] = np.asarray(loc["centrality"])
+            payload[f"{name}_W_all"] = np.asarray(loc["W_all"])
+            meta[f"{name}_scalars"] = {
+                "eff_edge_floor": float(loc["eff_edge_floor"]),
+                "k_eff_all": int(loc["k_eff_all"]),
+                "eff_tau_merge": float(loc["eff_tau_merge"]) if "eff_tau_merge" in loc else None,
+                "eff_reassign_delta": float(loc["eff_reassign_delta"]) if "eff_reassign_delta" in loc else None,
+                "global_merge_thr": float(loc["global_merge_thr"]) if "global_merge_thr" in loc else None,
+                "mu": float(loc["mu"]), "sigma": float(loc["sigma"]),
+                "method_used": str(loc["method_used"]),
+            }
+        meta[f"{name}_chunks"] = [[cid, m] for (cid, _t, m) in out]
+    payload["meta_json"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(OUT_DIR, "grouping.npz"), **payload)
+
+
+def gen_splitter(ref):
+    rng = np.random.default_rng(303)
+    payload = {}
+    meta = {}
+    for name, n, d, kwargs in (("s40", 40, 32, {}), ("s97", 97, 24, {"c99_use_local_rank": True}),
+                               ("s12", 12, 16, {}), ("s3", 3, 16, {})):
+        E = topic_doc(rng, n, d, sent_per_topic=9, noise=0.6)
+        text, sents = ref_shim.make_doc(E, tag=name)
+        names = ("embeddings", "adj_sims", "adj_base", "adj_for_valley", "valley_tau", "c99_bounds",
+                 "valley_bounds", "S", "R", "min_boundary_spacing", "min_first_boundary_index")
+        (chunks, sentences, groups), grabbed = capture_locals(
+            ref.split.process_sentence_splitting_with_semantics, names,
+            {"process_sentence_splitting_with_semantics", "_c99_boundaries"},
+            text, embedding_model="m", device="cpu", silent=True, **kwargs)
+        main = grabbed.get("process_sentence_splitting_with_semantics", {})
+        c99 = grabbed.get("_c99_boundaries", {})
+        payload[f"{name}_E"] = E
+        payload[f"{name}_En"] = np.asarray(main["embeddings"])
+        payload[f"{name}_adj_sims"] = np.asarray(main["adj_sims"], dtype=np.float64)
+        payload[f"{name}_adj_base"] = np.asarray(main["adj_base"], dtype=np.float64)
+        payload[f"{name}_adj_for_valley"] = np.asarray(main["adj_for_valley"], dtype=np.float64)
+        if "S" in c99:
+            payload[f"{name}_c99_S"] = np.asarray(c99["S"])
+            payload[f"{name}_c99_R"] = np.asarray(c99["R"])
+        meta[name] = {
+            "kwargs": kwargs,
+            "valley_tau": float(main["valley_tau"]),
+            "c99_bounds": [int(x) for x in main["c99_bounds"]],
+            "valley_bounds": [int(x) for x in main["valley_bounds"]],
+            "groups": [[int(g[0]), int(g[-1])] for g in groups],
+            "min_boundary_spacing": int(main["min_boundary_spacing"]),
+            "min_first_boundary_index": int(main["min_first_boundary_index"]),
+        }
+    payload["meta_json"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(OUT_DIR, "splitter.npz"), **payload)
+
+
+def main():
+    ref = ref_shim.load_reference()
+    if ref is None:
+        raise SystemExit("reference tree not present; golden vectors can only be generated in the build container")
+    os.makedirs(OUT_DIR, exist_ok=True)
+    gen_rank(ref)
+    gen_simmatrix_and_grouping(ref)
+    gen_splitter(ref)
+    print("wrote", sorted(os.listdir(OUT_DIR)))
+
+
+if __name__ == "__main__":
+    main()

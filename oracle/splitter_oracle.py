@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE — oracle for the semantic-splitter similarity passes.
+
+Restates the dense arithmetic of Method/Semantic_Splitter_Optimized.py: ``_embed``'s
+normalisation ``:140-152``, adjacent-sentence similarity ``:412``, ``_median_smooth``
+``:340-356``, the robust MAD/IQR sigmoid ``:417-437`` (+ valley tau ``:465``), and the C99
+similarity / rank matrices ``:169-192``.  BASELINE.json config 3's "95th-percentile
+breakpoints" has no counterpart in the reference; it is pinned to numpy as
+``d = 1 - adj``, ``thr = np.percentile(d, 95)``, ``breakpoints = where(d > thr)``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from .simmatrix_oracle import normalize_rows_1e9
+
+
+def adjacent_sims_ref(E: np.ndarray) -> np.ndarray:
+    """Splitter:412 — ``float(En[i] @ En[i+1])`` for i < n-1 (fp32 dot widened to fp64)."""
+    En = normalize_rows_1e9(np.asarray(E))
+    n = En.shape[0]
+    return np.array([float(En[i] @ En[i + 1]) for i in range(n - 1)], dtype=float)
+
+
+def median_smooth_ref(arr, window: int = 3) -> List[float]:
+    """Splitter:340-356 — odd window, edge-replicated padding, ``np.median`` per window."""
+    w = int(window)
+    arr = list(arr)
+    if w <= 1:
+        return arr
+    if w % 2 == 0:
+        w += 1
+    n = len(arr)
+    if n == 0 or w > max(1, n):
+        return arr
+    half = w // 2
+    padded = [arr[0]] * half + arr + [arr[-1]] * half
+    return [float(np.median(padded[i:i + w])) for i in range(n)]
+
+
+def robust_stats_ref(adj_sims, smooth_window: int = 3) -> Dict[str, object]:
+    """Splitter:417-437,465 (auto_params path): smoothed series, median, MAD+1e-9, IQR,
+    ``tau = max(IQR/2, 0.05)``, ``sigmoid((x-med)/MAD / tau)``, ``valley_tau = max(IQR/2, 0.06)``."""
+    adj_base = median_smooth_ref(adj_sims, smooth_window) if smooth_window and smooth_window > 1 else list(adj_sims)
+    x = np.array(adj_base, dtype=float)
+    med = float(np.median(x)) if x.size else 0.0
+    mad = float(np.median(np.abs(x - med)) + 1e-9) if x.size else 1e-9
+    iqr = float(np.percentile(x, 75) - np.percentile(x, 25)) if x.size else 0.0
+    tau = max(iqr / 2.0, 0.05)
+    z = (x - med) / mad
+    with np.errstate(over="ignore"):
+        sig = 1.0 / (1.0 + np.exp(-(z / tau)))
+    return {"adj_base": x, "median": med, "mad": mad, "iqr": iqr, "tau": tau,
+            "adj_for_valley": sig, "valley_tau": max(iqr / 2.0, 0.06)}
+
+
+def p95_breakpoints_ref(adj_sims, pct: float = 95.0) -> Tuple[float, np.ndarray]:
+    """BASELINE.json config 3 rule: distance = 1 - adj; threshold = np.percentile(d, pct)
+    (linear interpolation); breakpoints = indices with d > threshold."""
+    d = 1.0 - np.asarray(adj_sims, dtype=float)
+    if d.size == 0:
+        return float("nan"), np.zeros(0, dtype=np.int64)
+    thr = float(np.percentile(d, pct))
+    return thr, np.nonzero(d > thr)[0]
+
+
+def segmented_splitter_pass_ref(E: np.ndarray, offsets: np.ndarray, pct: float = 95.0):
+    """Whole ragged batch: per document adjacent sims, P-th percentile distance threshold and
+    breakpoint flags, concatenated in the layout the CUDA pass emits (one slot per row; the
+    last row of each document carries adj = 0 / flag = 0)."""
+    E = np.asarray(E)
+    total = E.shape[0]
+    adj = np.zeros(total, dtype=np.float32)
+    flags = np.zeros(total, dtype=np.uint8)
+    thr = np.full(len(offsets) - 1, np.nan, dtype=np.float64)
+    for di, (a, b) in enumerate(zip(offsets[:-1], offsets[1:])):
+        a, b = int(a), int(b)
+        if b - a < 2:
+            continue
+        sims = adjacent_sims_ref(E[a:b])
+        adj[a:b - 1] = sims.astype(np.float32)
+        t, bp = p95_breakpoints_ref(sims, pct)
+        thr[di] = t
+        flags[a + bp] = 1
+    return adj, thr, flags
+
+
+def c99_similarity_ref(En: np.ndarray) -> np.ndarray:
+    """Splitter:169 — ``S = embs @ embs.T`` on already-normalised embeddings."""
+    En = np.asarray(En)
+    return En @ En.T
+
+
+def c99_global_rank_ref(S: np.ndarray) -> np.ndarray:
+    """Splitter:189-192 — R[i,j] = #{k: S[i,k] < S[i,j]} + #{k: S[k,j] < S[i,j]} as fp32."""
+    S = np.asarray(S)
+    row_less = (S[:, None, :] < S[:, :, None]).sum(axis=2).astype(np.int32)
+    col_less = (S.T[:, None, :] < S.T[:, :, None]).sum(axis=2).astype(np.int32).T
+    return (row_less + col_less).astype(np.float32)
+
+
+def c99_local_rank_ref(S: np.ndarray, mask_size: int = 11) -> np.ndarray:
+    """Splitter:171-186 — fraction of the clipped m x m window strictly below S[i,j]."""
+    S = np.asarray(S)
+    n = S.shape[0]
+    m = max(3, int(mask_size) | 1)
+    half = m // 2
+    R = np.zeros_like(S, dtype=np.float32)
+    for i in range(n):
+        i0, i1 = max(0, i - half), min(n, i + half + 1)
+        for j in range(n):
+            j0, j1 = max(0, j - half), min(n, j + half + 1)
+            win = S[i0:i1, j0:j1]
+            R[i, j] = float((win < S[i, j]).sum()) / float(win.size if win.size else 1)
+    return R
