@@ -1,0 +1,120 @@
+"""Host-side operators over the C ABI: torch is used for device memory, streams and nothing else.
+
+Every function here takes CUDA tensors, passes raw device pointers + the current stream to
+``libsemsearch_b200.so`` and returns CUDA tensors.  No function has a CPU code path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.SS_F32, torch.bfloat16: _lib.SS_BF16, torch.float16: _lib.SS_F16}
+
+_workspaces: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; expected float32, bfloat16 or float16") from None
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError("semanticsearch_b200 operators require CUDA tensors (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("all tensors must live on the same CUDA device")
+    return dev
+
+
+def _stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def workspace(dev: torch.device, nbytes: int, tag: str = "default") -> torch.Tensor:
+    """Grow-only per-device scratch buffer (caller-provided workspace of the C ABI)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+        _workspaces[key] = buf
+    return buf
+
+
+def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_base: int = 0,
+                return_keys: bool = False):
+    """Top-k cosine similarity of each query row against every corpus row.
+
+    Device form of ``cosine_similarity(q, C)[0]`` + ``np.argsort(-s)[:k]``
+    (Tool/rank_chunks_optimized.py:215-216,225).  Returns ``(scores fp32 [B,k], indices int64
+    [B,k])`` best-first, ties resolved to the lower index; with ``return_keys`` also the packed
+    int64 keys used for multi-GPU merging.
+    """
+    dev = _require_cuda(corpus, queries)
+    if corpus.dim() != 2 or queries.dim() != 2 or corpus.shape[1] != queries.shape[1]:
+        raise ValueError(f"shape mismatch: corpus {tuple(corpus.shape)} vs queries {tuple(queries.shape)}")
+    if not corpus.is_contiguous() or not queries.is_contiguous():
+        raise ValueError("corpus and queries must be contiguous row-major tensors")
+    n, d = corpus.shape
+    b = queries.shape[0]
+    k = int(k)
+    if k <= 0 or n <= 0 or b <= 0:
+        raise ValueError("k, corpus rows and query rows must be positive")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        need = lib.ss_cosine_topk_stream_workspace_bytes(n, d, _dtype_code(corpus), b, k)
+        ws = workspace(dev, need)
+        scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((b, k), dtype=torch.int64, device=dev)
+        keys = torch.empty((b, k), dtype=torch.int64, device=dev) if return_keys else None
+        st = lib.ss_cosine_topk_stream(
+            corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, _dtype_code(queries), k,
+            int(index_base), ws.data_ptr(), ws.numel(), keys.data_ptr() if keys is not None else None,
+            scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
+        _lib.check(st, "ss_cosine_topk_stream")
+    if return_keys:
+        return scores, idx, keys
+    return scores, idx
+
+
+def topk_merge(keys: torch.Tensor, k_out: Optional[int] = None):
+    """Merge ``keys[P, B, k]`` (P best-first lists per query) into the global top ``k_out``.
+
+    Used after the NCCL all-gather of per-GPU results; returns ``(scores, indices, keys)``.
+    """
+    dev = _require_cuda(keys)
+    if keys.dim() != 3 or keys.dtype != torch.int64 or not keys.is_contiguous():
+        raise ValueError("keys must be a contiguous int64 tensor of shape [lists, queries, k]")
+    p, b, k_in = keys.shape
+    k_out = int(k_out or k_in)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        scores = torch.empty((b, k_out), dtype=torch.float32, device=dev)
+        idx = torch.empty((b, k_out), dtype=torch.int64, device=dev)
+        out_keys = torch.empty((b, k_out), dtype=torch.int64, device=dev)
+        st = lib.ss_topk_merge(keys.data_ptr(), p, b, k_in, k_in, b * k_in, k_out, out_keys.data_ptr(),
+                               scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
+        _lib.check(st, "ss_topk_merge")
+    return scores, idx, out_keys
+
+
+def row_inv_norms(rows: torch.Tensor, zero_value: float = 1.0) -> torch.Tensor:
+    """``1/||row||`` in fp32; zero rows map to ``zero_value`` (1.0 = sklearn's rule)."""
+    dev = _require_cuda(rows)
+    if rows.dim() != 2 or not rows.is_contiguous():
+        raise ValueError("rows must be a contiguous 2-D tensor")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        out = torch.empty(rows.shape[0], dtype=torch.float32, device=dev)
+        st = lib.ss_row_inv_norms(rows.data_ptr(), rows.shape[0], rows.shape[1], _dtype_code(rows), float(zero_value),
+                                  out.data_ptr(), _stream_ptr(dev))
+        _lib.check(st, "ss_row_inv_norms")
+    return out
