@@ -294,7 +294,7 @@ def run_ours(args):
             "dtype": "bf16 storage, f32 accumulate", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": args.batch * args.dim * 2,
                     "d2h_bytes_per_step": args.batch * args.k * 12, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
+            "gpu_launches": args.steps * (1 + (1 if world > 1 else 0)),
             "roofline": roof, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
