@@ -84,6 +84,48 @@ int ss_topk_merge(const uint64_t* keys_in, int n_lists, int n_queries, int k_in,
 int ss_row_inv_norms(const void* rows, int64_t n_rows, int dim, int dtype, float zero_value,
                      float* out_inv_norms, void* stream);
 
+/* ---- K3: segmented sentence x sentence similarity matrices ------------------------------------
+ * For every document d (rows offsets[d]..offsets[d+1] of the fp32 matrix `rows`), S_d = En En^T with
+ * rows L2-normalised on the fly (zero rows -> zero row/column), written as a dense n_d x n_d fp32
+ * block at out_S + s_offsets[d].  Replaces the arithmetic of create_similarity_matrix
+ * (Method/semantic_common.py:158-164,186-191), Method/Semantic_Splitter_Optimized.py:169 and
+ * data_process/simple_chunk_controller.py:614,682,743.  ss_segmented_plan_host is pure host index
+ * arithmetic (HOST pointers): s_offsets = prefix sums of n^2, tile_prefix = prefix sums of
+ * T(T+1)/2 with T = ceil(n/64); the caller uploads both. */
+int ss_segmented_plan_host(const int32_t* offsets_host, int n_docs, int64_t* s_offsets_host,
+                           int32_t* tile_prefix_host, int64_t* total_tiles, int32_t* max_doc_rows);
+int ss_segmented_simmatrix(const float* rows, int dim, const int32_t* offsets, const int64_t* s_offsets,
+                           const int32_t* tile_prefix, int n_docs, int64_t total_tiles, float* out_S, void* stream);
+
+/* ---- K4: semantic-grouping threshold pass ------------------------------------------------------
+ * Per document, from S (layout of K3): sim_sharp = sigmoid(((S-mu)/sigma)/tau) in fp32 with zero
+ * diagonal (Method/Semantic_Grouping_Optimized.py:100-113), centrality (:115), the quantile
+ * thresholds of the positive entries q80/q65/q60 and 0.1*std (:351-355,458-462,534-537,559-561)
+ * and each row's top-(k_eff+1) neighbours, value-descending/index-ascending (:270-283; the >= floor
+ * filter and max-symmetrisation are applied by the caller).
+ * out_doc_stats[d] = {mu, sigma, q80, q65, q60, 0.1*std(pos), count(pos), k}; out_knn_* are
+ * [total_rows][33] (-1 / 0 padded).  knn_mode: 0 = auto k (:347), >0 = explicit knn_k (<= 32),
+ * -1 = max(5, min(20, n-1)) (:349). */
+int ss_group_threshold_pass(const float* S, const int32_t* offsets, const int64_t* s_offsets, int n_docs, float tau,
+                            int knn_mode, float* out_sharp, double* out_centrality, double* out_doc_stats,
+                            int32_t* out_knn_idx, float* out_knn_val, void* stream);
+
+/* ---- K5: semantic-splitter passes over ragged documents ---------------------------------------
+ * Documents are concatenated: rows = [total_rows x dim]; offsets = int32[n_docs+1] (device) CSR
+ * row offsets.
+ * ss_segmented_adjacent_cosine: out_adj[r] = cos(rows[r], rows[r+1]) (rows L2-normalised on the
+ * fly, zero rows -> 0), one streaming pass; replaces `_embed` + the adjacent dot loop at
+ * Method/Semantic_Splitter_Optimized.py:140-152,412.  The slot of each document's last row is
+ * zeroed by ss_segmented_percentile.
+ * ss_segmented_percentile: per document d = 1 - adj, out_thr[doc] = np.percentile(d, pct)
+ * (linear interpolation, fp64), out_flags[r] = d[r] > thr (BASELINE.json config 3 breakpoints);
+ * optional out_smooth[r] = median-of-3 smoothed adj (Splitter:340-356) and out_stats[doc] =
+ * {median, MAD + 1e-9, P25, P75} of the smoothed series (Splitter:417-437).  Documents with a
+ * single row get thr = NaN.  max_doc_rows bounds the per-document shared-memory sort (<= 8193). */
+int ss_segmented_adjacent_cosine(const void* rows, int64_t n_rows, int dim, int dtype, float* out_adj, void* stream);
+int ss_segmented_percentile(float* adj, const int32_t* offsets, int n_docs, int max_doc_rows, double pct,
+                            double* out_thr, uint8_t* out_flags, double* out_stats, float* out_smooth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

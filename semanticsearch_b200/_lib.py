@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsemsearch_b200.so")
@@ -30,6 +30,13 @@ _SIGNATURES = {
                                       c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ss_topk_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
+    "ss_segmented_plan_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int)]),
+    "ss_segmented_simmatrix": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "ss_group_threshold_pass": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "ss_segmented_adjacent_cosine": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "ss_segmented_percentile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
     "ss_row_inv_norms": (c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 

@@ -176,83 +176,6 @@ __device__ __forceinline__ void cta_epilogue(const StreamParams& p, const uint64
 // ------------------------------------------------------------------------------------------
 // Main kernel
 // ------------------------------------------------------------------------------------------
-// Packed fp32 pair math (Blackwell FFMA2): halves the FMA instruction count of the row pass.
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ float sum2(unsigned long long v) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-  return lo + hi;
-}
-
-// One 16-byte chunk -> EPC/2 packed fp32 pairs.
-template <typename T>
-struct Pairs;
-template <>
-struct Pairs<float> {
-  static constexpr int NP = 2;
-  __device__ __forceinline__ static void unpack(const uint4& r, unsigned long long* x) {
-    x[0] = (static_cast<unsigned long long>(r.y) << 32) | r.x;
-    x[1] = (static_cast<unsigned long long>(r.w) << 32) | r.z;
-  }
-};
-template <>
-struct Pairs<__nv_bfloat16> {
-  static constexpr int NP = 4;
-  __device__ __forceinline__ static void unpack(const uint4& r, unsigned long long* x) {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
-  }
-};
-template <>
-struct Pairs<__half> {
-  static constexpr int NP = 4;
-  __device__ __forceinline__ static void unpack(const uint4& r, unsigned long long* x) {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-      x[i] = pack2(f.x, f.y);
-    }
-  }
-};
-
-constexpr int next_pow2(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : (v <= 16 ? 16 : 32)))); }
-constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
-
-// Transposing butterfly: NVP per-lane partial sums -> one fully reduced value per lane.
-// Afterwards lane L holds value index (L >> (5 - log2 NVP)); ~NVP + log2(32/NVP) shuffles in
-// total instead of 5 * NVP.
-template <int NVP>
-__device__ __forceinline__ float transpose_reduce(float (&v)[NVP], int lane) {
-  int off = 16;
-#pragma unroll
-  for (int n = NVP; n > 1; n >>= 1) {
-    const int half = n >> 1;
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = upper ? v[i] : v[i + half];
-      const float keep = upper ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-    off >>= 1;
-  }
-  float r = v[0];
-#pragma unroll
-  for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
-  return r;
-}
-
 // R corpus rows per warp iteration, BT queries; QREG keeps the (single) query in registers.
 template <typename T, int BT, int R, bool QREG>
 __global__ void __launch_bounds__(kStreamThreads, 1) cosine_topk_stream_kernel(const StreamParams p) {

@@ -1,0 +1,161 @@
+"""Host-side operators for ragged (per-document) batches: K3 similarity matrices, K4 grouping
+threshold pass, K5 splitter passes.  Documents are concatenated row-wise; a ``RaggedPlan`` holds
+the CSR offsets and the derived index arrays on the device.  No CPU code path exists here.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .similarity import _dtype_code, _require_cuda, _stream_ptr
+
+KNN_WIDTH = 33
+
+
+@dataclass
+class RaggedPlan:
+    offsets: np.ndarray        # int32 [D+1] (host)
+    s_offsets: np.ndarray      # int64 [D+1] (host) prefix sums of n^2
+    tile_prefix: np.ndarray    # int32 [D+1] (host)
+    total_tiles: int
+    max_rows: int
+    offsets_d: torch.Tensor
+    s_offsets_d: torch.Tensor
+    tile_prefix_d: torch.Tensor
+
+    @property
+    def n_docs(self) -> int:
+        return len(self.offsets) - 1
+
+    @property
+    def total_rows(self) -> int:
+        return int(self.offsets[-1])
+
+    @property
+    def total_s(self) -> int:
+        return int(self.s_offsets[-1])
+
+    def sizes(self) -> np.ndarray:
+        return np.diff(self.offsets)
+
+
+def make_plan(sizes: Sequence[int], device) -> RaggedPlan:
+    """Index arrays for a batch of documents with ``sizes[d]`` sentences each."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    if sizes.ndim != 1 or sizes.size == 0 or (sizes < 0).any():
+        raise ValueError("sizes must be a non-empty 1-D array of non-negative sentence counts")
+    if int(sizes.sum()) >= 2 ** 31:
+        raise ValueError("more than 2^31 rows in one ragged batch")
+    offsets = np.zeros(sizes.size + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum(sizes)
+    s_off = np.zeros(sizes.size + 1, dtype=np.int64)
+    tile_prefix = np.zeros(sizes.size + 1, dtype=np.int32)
+    total = ctypes.c_int64()
+    mx = ctypes.c_int()
+    lib = _lib.load()
+    st = lib.ss_segmented_plan_host(offsets.ctypes.data, int(sizes.size), s_off.ctypes.data, tile_prefix.ctypes.data,
+                                    ctypes.byref(total), ctypes.byref(mx))
+    _lib.check(st, "ss_segmented_plan_host")
+    dev = torch.device(device)
+    return RaggedPlan(offsets, s_off, tile_prefix, int(total.value), int(mx.value),
+                      torch.from_numpy(offsets).to(dev), torch.from_numpy(s_off).to(dev),
+                      torch.from_numpy(tile_prefix).to(dev))
+
+
+def segmented_simmatrix(E: torch.Tensor, plan: RaggedPlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """All per-document ``S = En @ En.T`` blocks, packed (Method/semantic_common.py:158-191)."""
+    dev = _require_cuda(E)
+    if E.dtype != torch.float32 or E.dim() != 2 or not E.is_contiguous():
+        raise ValueError("E must be a contiguous float32 [total_rows, dim] tensor")
+    if E.shape[0] != plan.total_rows:
+        raise ValueError(f"E has {E.shape[0]} rows, plan expects {plan.total_rows}")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty(plan.total_s, dtype=torch.float32, device=dev)
+        elif out.numel() < plan.total_s or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError("out must be a CUDA float32 tensor with at least plan.total_s elements")
+        st = lib.ss_segmented_simmatrix(E.data_ptr(), E.shape[1], plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(),
+                                        plan.tile_prefix_d.data_ptr(), plan.n_docs, plan.total_tiles, out.data_ptr(),
+                                        _stream_ptr(dev))
+        _lib.check(st, "ss_segmented_simmatrix")
+    return out
+
+
+def group_threshold_pass(S: torch.Tensor, plan: RaggedPlan, tau: float = 0.15, knn_mode: int = 0) -> Dict[str, torch.Tensor]:
+    """Grouping threshold pass for every document (Method/Semantic_Grouping_Optimized.py:100-115,
+    270-283,343-360).  Returns device tensors: sim_sharp (packed), centrality [rows] f64,
+    doc_stats [D,8] f64 = (mu, sigma, q80, q65, q60, 0.1*std, count, k), knn_idx/knn_val [rows,33]."""
+    dev = _require_cuda(S)
+    if S.dtype != torch.float32 or not S.is_contiguous() or S.numel() < plan.total_s:
+        raise ValueError("S must be the packed float32 output of segmented_simmatrix")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        sharp = torch.empty(plan.total_s, dtype=torch.float32, device=dev)
+        cent = torch.empty(plan.total_rows, dtype=torch.float64, device=dev)
+        stats = torch.empty((plan.n_docs, 8), dtype=torch.float64, device=dev)
+        kidx = torch.empty((plan.total_rows, KNN_WIDTH), dtype=torch.int32, device=dev)
+        kval = torch.empty((plan.total_rows, KNN_WIDTH), dtype=torch.float32, device=dev)
+        st = lib.ss_group_threshold_pass(S.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), plan.n_docs,
+                                         float(tau), int(knn_mode), sharp.data_ptr(), cent.data_ptr(), stats.data_ptr(),
+                                         kidx.data_ptr(), kval.data_ptr(), _stream_ptr(dev))
+        _lib.check(st, "ss_group_threshold_pass")
+    return {"sim_sharp": sharp, "centrality": cent, "doc_stats": stats, "knn_idx": kidx, "knn_val": kval}
+
+
+def adjacent_cosine(E: torch.Tensor) -> torch.Tensor:
+    """``adj[r] = cos(E[r], E[r+1])`` for the whole concatenated matrix
+    (Method/Semantic_Splitter_Optimized.py:140-152,412); the last row gets 0."""
+    dev = _require_cuda(E)
+    if E.dim() != 2 or not E.is_contiguous():
+        raise ValueError("E must be a contiguous 2-D tensor")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        out = torch.empty(E.shape[0], dtype=torch.float32, device=dev)
+        st = lib.ss_segmented_adjacent_cosine(E.data_ptr(), E.shape[0], E.shape[1], _dtype_code(E), out.data_ptr(),
+                                              _stream_ptr(dev))
+        _lib.check(st, "ss_segmented_adjacent_cosine")
+    return out
+
+
+def segmented_percentile(adj: torch.Tensor, plan: RaggedPlan, pct: float = 95.0, want_stats: bool = True):
+    """Per-document percentile threshold of ``1 - adj`` + breakpoint flags (BASELINE.json cfg 3)
+    and, optionally, the splitter's robust statistics (Splitter:340-356,417-437).
+    Returns ``(thr [D] f64, flags [rows] u8, stats [D,4] f64 | None, smooth [rows] f32 | None)``;
+    stats columns are (median, MAD+1e-9, P25, P75) of the median-of-3 smoothed series.
+    ``adj`` is updated in place: the slot of each document's last sentence is set to 0."""
+    dev = _require_cuda(adj)
+    if adj.dtype != torch.float32 or adj.dim() != 1 or not adj.is_contiguous() or adj.numel() != plan.total_rows:
+        raise ValueError("adj must be the float32 [total_rows] output of adjacent_cosine")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        thr = torch.empty(plan.n_docs, dtype=torch.float64, device=dev)
+        flags = torch.empty(plan.total_rows, dtype=torch.uint8, device=dev)
+        stats = torch.empty((plan.n_docs, 4), dtype=torch.float64, device=dev) if want_stats else None
+        smooth = torch.empty(plan.total_rows, dtype=torch.float32, device=dev) if want_stats else None
+        st = lib.ss_segmented_percentile(adj.data_ptr(), plan.offsets_d.data_ptr(), plan.n_docs, max(plan.max_rows, 1),
+                                         float(pct), thr.data_ptr(), flags.data_ptr(),
+                                         stats.data_ptr() if want_stats else None,
+                                         smooth.data_ptr() if want_stats else None, _stream_ptr(dev))
+        _lib.check(st, "ss_segmented_percentile")
+    return thr, flags, stats, smooth
+
+
+def knn_graph_from_lists(knn_idx: np.ndarray, knn_val: np.ndarray, floor: float) -> np.ndarray:
+    """Dense symmetric ``W`` of one document from its neighbour lists — the tail of
+    ``_build_knn_graph`` (Grouping:277-283): drop self, keep ``val >= floor``, ``max(W, W.T)``.
+    Pure indexing on a few hundred entries per document; stays on the host next to the
+    sequential clustering that consumes ``W``."""
+    n = knn_idx.shape[0]
+    W = np.zeros((n, n), dtype=float)
+    rows = np.repeat(np.arange(n), knn_idx.shape[1])
+    cols = knn_idx.reshape(-1).astype(np.int64)
+    vals = knn_val.reshape(-1).astype(float)
+    keep = (cols >= 0) & (cols != rows) & (vals >= floor)
+    W[rows[keep], cols[keep]] = vals[keep]
+    return np.maximum(W, W.T)
