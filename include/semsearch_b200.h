@@ -69,6 +69,18 @@ int ss_cosine_topk_stream(const void* corpus, int64_t n_rows, int dim, int corpu
                           uint64_t* out_keys, float* out_scores, int64_t* out_indices,
                           void* stream);
 
+/* ---- K2: tensor-core cosine + fused top-k, large query batches ---------------------------------
+ * Same contract as ss_cosine_topk_stream for bf16/fp16 corpora and queries of the same dtype, k <= 16,
+ * dim % 8 == 0: D = Q C^T on tcgen05 tensor cores (TMA-fed shared-memory operands, fp32
+ * accumulators in TMEM), corpus/query inverse norms applied and the top-k selected in the
+ * accumulator epilogue; the B x N score matrix is never materialised.  Replaces the same reference
+ * lines (Tool/rank_chunks_optimized.py:215-216,225-235) when many queries are ranked at once. */
+size_t ss_cosine_topk_gemm_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k);
+int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, int dtype,
+                        const void* queries, int n_queries, int k, uint32_t index_base,
+                        void* workspace, size_t workspace_bytes,
+                        uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
+
 /* ---- K6: k-way merge of best-first key lists ------------------------------------------------
  * Merges n_lists sorted lists per query (per-CTA partials, or per-GPU results after an NCCL
  * all-gather) into the global top k_out.  key(q, p, j) = keys_in[q*query_stride + p*list_stride + j].

@@ -1,0 +1,477 @@
+// K2 — query-batch cosine similarity on the 5th-gen tensor cores with a fused top-k epilogue.
+//
+// Replaces sklearn.cosine_similarity(Q, C) + np.argsort(-s) (Tool/rank_chunks_optimized.py:215-216,
+// 225-235) when the query batch makes the work a real GEMM.  D[query, corpus_row] = Q . C^T with
+// bf16/fp16 operands and fp32 accumulation:
+//
+//   warp 0   TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of a 128 x 64 query tile and a
+//                           256 x 64 corpus tile per K block into a 4-stage shared-memory ring
+//   warp 1   MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=256, K=16) on shared
+//                           memory descriptors; accumulators live in TMEM, double-buffered
+//                           (2 x 256 columns) so the next tile's MMAs overlap this tile's epilogue
+//   warps 2-5 epilogue    : tcgen05.ld the 128 x 256 accumulator tile (one query row per thread),
+//                           scale by 1/|c| (shared-memory broadcast) and 1/|q|, threshold against
+//                           the thread's current k-th best and keep a sorted top-k in registers.
+//
+// The B x N score matrix is never written.  Work is split into (query block, corpus chunk) units
+// so that all query blocks of one chunk run concurrently and share corpus tiles through L2; each
+// unit writes k packed keys per query and ss_topk_merge folds the chunks.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "ss_common.cuh"
+
+namespace ss {
+
+constexpr int G_BM = 128;
+constexpr int G_BN = 256;
+constexpr int G_BK = 64;
+constexpr int G_STAGES = 4;
+constexpr int G_A_BYTES = G_BM * G_BK * 2;
+constexpr int G_B_BYTES = G_BN * G_BK * 2;
+constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_THREADS = 192;
+constexpr int G_EPI_THREADS = 128;
+constexpr int G_TMEM_COLS = 512;
+
+struct GemmParams {
+  int n_queries;
+  long long n_rows;
+  int dim;
+  int k;
+  uint32_t index_base;
+  int n_qb;
+  long long n_tiles;
+  int tiles_per_chunk;
+  int n_chunks;
+  long long n_units;
+  const float* inv_c;
+  const float* inv_q;
+  uint64_t* partial;  // [n_chunks][n_queries][k]
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; single-thread issue.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand stored as rows of 128 bytes (64 bf16/fp16)
+// with the 128-byte swizzle TMA writes: 8-row groups are 1024 bytes apart (SBO), descriptor
+// version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor fields.)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);  // start address, 16-byte units
+  d |= static_cast<uint64_t>(1) << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+  d |= static_cast<uint64_t>(1) << 46;                     // descriptor version
+  d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A/B format, K-major both.
+__host__ __device__ constexpr uint32_t make_idesc(int ab_format, int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(ab_format) << 7) | (static_cast<uint32_t>(ab_format) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// Sorted (descending) insertion into a register-resident top-KT list; strict '>' keeps the
+// earlier (lower-index) entry first among equal scores.
+template <int KT>
+__device__ __forceinline__ void list_insert_sorted(float (&v)[KT], int (&ix)[KT], float t, int c) {
+#pragma unroll
+  for (int j = KT - 1; j >= 1; --j) {
+    const bool up = t > v[j - 1];
+    const bool here = !up && (t > v[j]);
+    const float nv = up ? v[j - 1] : (here ? t : v[j]);
+    const int ni = up ? ix[j - 1] : (here ? c : ix[j]);
+    v[j] = nv;
+    ix[j] = ni;
+  }
+  if (t > v[0]) {
+    v[0] = t;
+    ix[0] = c;
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(G_THREADS, 1)
+cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                        const GemmParams p, const uint32_t idesc) {
+  extern __shared__ unsigned char gemm_smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
+  unsigned char* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + G_STAGES * G_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G_STAGES;
+  uint64_t* tmem_full = empty_bar + G_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sinv = reinterpret_cast<float*>(tmem_ptr_s + 4);  // [2][G_BN] corpus inverse norms of the tile in flight
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.dim + G_BK - 1) / G_BK;
+
+  if (threadIdx.x == 0) {
+    tmap_prefetch(&tmap_q);
+    tmap_prefetch(&tmap_c);
+    for (int s = 0; s < G_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_s, G_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int chunk = static_cast<int>(u / p.n_qb), qb = static_cast<int>(u % p.n_qb);
+        const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
+        const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+        for (long long t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[s], G_STAGE_BYTES);
+            unsigned char* a_dst = tiles + s * G_STAGE_BYTES;
+            tma_load_2d(a_dst, &tmap_q, &full_bar[s], kb * G_BK, qb * G_BM);
+            tma_load_2d(a_dst + G_A_BYTES, &tmap_c, &full_bar[s], kb * G_BK, static_cast<int>(t * G_BN));
+            if (++s == G_STAGES) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int s = 0, acc = 0;
+    uint32_t ph = 0, acc_ph = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int chunk = static_cast<int>(u / p.n_qb);
+      const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
+      const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+      for (long long t = t0; t < t1; ++t) {
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * G_BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);  // TMA bytes have landed
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(tiles + s * G_STAGE_BYTES);
+            const uint64_t da = make_smem_desc(a_addr);
+            const uint64_t db = make_smem_desc(a_addr + G_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < G_BK / 16; ++k)  // +32 bytes (2 x 16-byte units) per K=16 step inside the swizzle atom
+              umma_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[s]);                      // frees the smem stage when these MMAs retire
+            if (kb == nkb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          }
+          __syncwarp();
+          if (++s == G_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_ph ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: one query row per thread =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // query row inside the 128-row block
+    const int et = (warp - 2) * 32 + lane;     // 0..127 among epilogue threads
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int chunk = static_cast<int>(u / p.n_qb), qb = static_cast<int>(u % p.n_qb);
+      const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
+      const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+      const int query = qb * G_BM + row;
+      const float inv_q = query < p.n_queries ? p.inv_q[query] : 0.f;
+      float v[KT];
+      int ix[KT];
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        v[j] = -INFINITY;
+        ix[j] = -1;
+      }
+      float thr = -INFINITY;
+      for (long long t = t0; t < t1; ++t) {
+        // stage this tile's corpus inverse norms (NaN for rows past the end: never selected)
+        float* inv_tile = sinv + acc * G_BN;
+        for (int c = et; c < G_BN; c += G_EPI_THREADS) {
+          const long long gr = t * G_BN + c;
+          inv_tile[c] = gr < p.n_rows ? p.inv_c[gr] : __int_as_float(0x7fc00000);
+        }
+        epi_bar_sync();
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * G_BN);
+        const int col_base = static_cast<int>(t * G_BN);
+#pragma unroll 1
+        for (int c0 = 0; c0 < G_BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + static_cast<uint32_t>(c0), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sc = (__uint_as_float(r[j]) * inv_tile[c0 + j]) * inv_q;
+            if (sc > thr) {
+              list_insert_sorted<KT>(v, ix, sc, col_base + c0 + j);
+              thr = v[KT - 1];
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_ph ^= 1u;
+        }
+      }
+      if (query < p.n_queries) {
+        uint64_t* out = p.partial + (static_cast<size_t>(chunk) * p.n_queries + query) * p.k;
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (j < p.k) out[j] = ix[j] >= 0 ? make_key(v[j], p.index_base + static_cast<uint32_t>(ix[j])) : 0ull;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, G_TMEM_COLS);
+  }
+}
+
+// ---- vectorised row inverse norms (pre-pass over the corpus, HBM-bound) -------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) row_inv_norms_vec_kernel(const T* __restrict__ rows, long long n_rows, int dim,
+                                                                float zero_value, float* __restrict__ out) {
+  constexpr int NP = Pairs<T>::NP;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int chunks = dim * static_cast<int>(sizeof(T)) / 16;
+  for (long long r = warp * 2; r < n_rows; r += nwarps * 2) {
+    const uint4* ra = reinterpret_cast<const uint4*>(rows + static_cast<size_t>(r) * dim);
+    const bool two = r + 1 < n_rows;
+    const uint4* rb = two ? reinterpret_cast<const uint4*>(rows + static_cast<size_t>(r + 1) * dim) : ra;
+    unsigned long long sa = 0ull, sb = 0ull;
+    for (int c = lane; c < chunks; c += 32) {
+      const uint4 xa = __ldg(ra + c), xb = __ldg(rb + c);
+      unsigned long long pa[NP], pb[NP];
+      Pairs<T>::unpack(xa, pa);
+      Pairs<T>::unpack(xb, pb);
+#pragma unroll
+      for (int e = 0; e < NP; ++e) {
+        sa = ffma2(pa[e], pa[e], sa);
+        sb = ffma2(pb[e], pb[e], sb);
+      }
+    }
+    const float fa = warp_sum(sum2(sa)), fb = warp_sum(sum2(sb));
+    if (lane == 0) {
+      out[r] = fa > 0.f ? 1.0f / sqrtf(fa) : zero_value;
+      if (two) out[r + 1] = fb > 0.f ? 1.0f / sqrtf(fb) : zero_value;
+    }
+  }
+}
+
+template <typename T>
+static cudaError_t launch_inv_norms_vec(const void* rows, long long n_rows, int dim, float zero_value, float* out, cudaStream_t st) {
+  const long long want = (n_rows + 15) / 16;
+  const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(sm_count()) * 16)));
+  row_inv_norms_vec_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(rows), n_rows, dim, zero_value, out);
+  return cudaGetLastError();
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || !sym) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+static bool make_tmap(CUtensorMap* map, const void* base, int dtype, long long rows, int dim, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(G_BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = dtype == SS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+struct GemmPlan {
+  int n_qb;
+  long long n_tiles;
+  int tiles_per_chunk;
+  int n_chunks;
+};
+
+static GemmPlan make_gemm_plan(long long n_rows, int n_queries) {
+  GemmPlan g;
+  g.n_qb = (n_queries + G_BM - 1) / G_BM;
+  g.n_tiles = (n_rows + G_BN - 1) / G_BN;
+  const long long target_units = static_cast<long long>(sm_count()) * 8;
+  long long n_chunks = std::max<long long>(1, (target_units + g.n_qb - 1) / g.n_qb);
+  n_chunks = std::min<long long>(n_chunks, std::max<long long>(1, g.n_tiles / 8));  // at least ~8 tiles per chunk
+  g.tiles_per_chunk = static_cast<int>((g.n_tiles + n_chunks - 1) / n_chunks);
+  g.n_chunks = static_cast<int>((g.n_tiles + g.tiles_per_chunk - 1) / g.tiles_per_chunk);
+  return g;
+}
+
+}  // namespace ss
+
+using namespace ss;
+
+extern "C" size_t ss_cosine_topk_gemm_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k) {
+  (void)dim;
+  if (n_rows <= 0 || n_queries <= 0 || k <= 0) return 0;
+  const GemmPlan g = make_gemm_plan(n_rows, n_queries);
+  return align_up(static_cast<size_t>(n_rows) * 4, 256) + align_up(static_cast<size_t>(n_queries) * 4, 256) +
+         align_up(static_cast<size_t>(g.n_chunks) * n_queries * k * 8, 256) + 256;
+}
+
+extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, int dtype, const void* queries, int n_queries,
+                                   int k, uint32_t index_base, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
+                                   float* out_scores, int64_t* out_indices, void* stream) {
+  if (!corpus || !queries || !workspace) return fail(SS_ERR_INVALID_ARG, "ss_cosine_topk_gemm: null pointer");
+  if (n_rows <= 0 || dim <= 0 || n_queries <= 0 || k <= 0) return fail(SS_ERR_INVALID_ARG, "ss_cosine_topk_gemm: sizes must be positive");
+  if (dtype != SS_BF16 && dtype != SS_F16) return fail(SS_ERR_UNSUPPORTED, "ss_cosine_topk_gemm: corpus and queries must be bf16 or fp16");
+  if (k > 16) return fail(SS_ERR_UNSUPPORTED, "ss_cosine_topk_gemm: k > 16 is not supported (use ss_cosine_topk_stream)");
+  if (dim % 8 != 0 || (reinterpret_cast<uintptr_t>(corpus) & 15) || (reinterpret_cast<uintptr_t>(queries) & 15))
+    return fail(SS_ERR_UNSUPPORTED, "ss_cosine_topk_gemm: rows must be 16-byte multiples and 16-byte aligned");
+  if (n_rows > 0x7FFFFFFFll || static_cast<uint64_t>(index_base) + static_cast<uint64_t>(n_rows) > 0xFFFFFFFFull)
+    return fail(SS_ERR_UNSUPPORTED, "ss_cosine_topk_gemm: row indices must fit in 32 bits");
+  if (workspace_bytes < ss_cosine_topk_gemm_workspace_bytes(n_rows, dim, n_queries, k))
+    return fail(SS_ERR_WORKSPACE, "ss_cosine_topk_gemm: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  unsigned char* ws = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+  float* inv_c = reinterpret_cast<float*>(ws);
+  ws += align_up(static_cast<size_t>(n_rows) * 4, 256);
+  float* inv_q = reinterpret_cast<float*>(ws);
+  ws += align_up(static_cast<size_t>(n_queries) * 4, 256);
+  uint64_t* partial = reinterpret_cast<uint64_t*>(ws);
+
+  cudaError_t e;
+  if (dtype == SS_BF16) {
+    e = launch_inv_norms_vec<__nv_bfloat16>(corpus, n_rows, dim, 1.0f, inv_c, st);
+    if (e == cudaSuccess) e = launch_inv_norms_vec<__nv_bfloat16>(queries, n_queries, dim, 1.0f, inv_q, st);
+  } else {
+    e = launch_inv_norms_vec<__half>(corpus, n_rows, dim, 1.0f, inv_c, st);
+    if (e == cudaSuccess) e = launch_inv_norms_vec<__half>(queries, n_queries, dim, 1.0f, inv_q, st);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "row_inv_norms_vec launch");
+
+  CUtensorMap tmap_q, tmap_c;
+  if (!make_tmap(&tmap_q, queries, dtype, n_queries, dim, G_BM) || !make_tmap(&tmap_c, corpus, dtype, n_rows, dim, G_BN))
+    return fail(SS_ERR_CUDA, "ss_cosine_topk_gemm: cuTensorMapEncodeTiled failed");
+
+  const GemmPlan g = make_gemm_plan(n_rows, n_queries);
+  GemmParams p;
+  p.n_queries = n_queries;
+  p.n_rows = n_rows;
+  p.dim = dim;
+  p.k = k;
+  p.index_base = index_base;
+  p.n_qb = g.n_qb;
+  p.n_tiles = g.n_tiles;
+  p.tiles_per_chunk = g.tiles_per_chunk;
+  p.n_chunks = g.n_chunks;
+  p.n_units = static_cast<long long>(g.n_chunks) * g.n_qb;
+  p.inv_c = inv_c;
+  p.inv_q = inv_q;
+  p.partial = partial;
+  const uint32_t idesc = make_idesc(dtype == SS_BF16 ? 1 : 0, G_BM, G_BN);
+  const size_t smem = static_cast<size_t>(G_STAGES) * G_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4;
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(sm_count(), p.n_units)));
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    ProfileScope prof(st);
+    kern<<<grid, G_THREADS, smem, st>>>(tmap_q, tmap_c, p, idesc);
+    return cudaGetLastError();
+  };
+  if (k <= 1) e = launch(cosine_topk_gemm_kernel<1>);
+  else if (k <= 4) e = launch(cosine_topk_gemm_kernel<4>);
+  else if (k <= 8) e = launch(cosine_topk_gemm_kernel<8>);
+  else if (k <= 10) e = launch(cosine_topk_gemm_kernel<10>);
+  else e = launch(cosine_topk_gemm_kernel<16>);
+  if (e != cudaSuccess) return cuda_fail(e, "cosine_topk_gemm launch");
+  return ss_topk_merge(partial, g.n_chunks, n_queries, k, k, static_cast<int64_t>(n_queries) * k, k, out_keys, out_scores,
+                       out_indices, stream);
+}

@@ -49,8 +49,17 @@ def workspace(dev: torch.device, nbytes: int, tag: str = "default") -> torch.Ten
     return buf
 
 
+GEMM_MIN_BATCH = 16  # from this many queries on, bf16/fp16 work goes to the tensor-core kernel
+
+
+def _gemm_eligible(corpus: torch.Tensor, queries: torch.Tensor, k: int) -> bool:
+    return (corpus.dtype in (torch.bfloat16, torch.float16) and queries.dtype == corpus.dtype and k <= 16
+            and corpus.shape[1] % 8 == 0 and corpus.data_ptr() % 16 == 0 and queries.data_ptr() % 16 == 0
+            and corpus.shape[0] < 2 ** 31)
+
+
 def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_base: int = 0,
-                return_keys: bool = False):
+                return_keys: bool = False, algo: str = "auto"):
     """Top-k cosine similarity of each query row against every corpus row.
 
     Device form of ``cosine_similarity(q, C)[0]`` + ``np.argsort(-s)[:k]``
@@ -68,18 +77,32 @@ def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_ba
     k = int(k)
     if k <= 0 or n <= 0 or b <= 0:
         raise ValueError("k, corpus rows and query rows must be positive")
+    if algo not in ("auto", "stream", "gemm"):
+        raise ValueError("algo must be 'auto', 'stream' or 'gemm'")
+    use_gemm = algo == "gemm" or (algo == "auto" and b >= GEMM_MIN_BATCH and _gemm_eligible(corpus, queries, k))
+    if use_gemm and not _gemm_eligible(corpus, queries, k):
+        raise ValueError("the tensor-core path needs bf16/fp16 corpus and queries of one dtype, k <= 16, dim % 8 == 0")
     lib = _lib.load()
     with torch.cuda.device(dev):
-        need = lib.ss_cosine_topk_stream_workspace_bytes(n, d, _dtype_code(corpus), b, k)
-        ws = workspace(dev, need)
         scores = torch.empty((b, k), dtype=torch.float32, device=dev)
         idx = torch.empty((b, k), dtype=torch.int64, device=dev)
         keys = torch.empty((b, k), dtype=torch.int64, device=dev) if return_keys else None
-        st = lib.ss_cosine_topk_stream(
-            corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, _dtype_code(queries), k,
-            int(index_base), ws.data_ptr(), ws.numel(), keys.data_ptr() if keys is not None else None,
-            scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
-        _lib.check(st, "ss_cosine_topk_stream")
+        if use_gemm:
+            need = lib.ss_cosine_topk_gemm_workspace_bytes(n, d, b, k)
+            ws = workspace(dev, need, "gemm")
+            st = lib.ss_cosine_topk_gemm(
+                corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, k, int(index_base), ws.data_ptr(),
+                ws.numel(), keys.data_ptr() if keys is not None else None, scores.data_ptr(), idx.data_ptr(),
+                _stream_ptr(dev))
+            _lib.check(st, "ss_cosine_topk_gemm")
+        else:
+            need = lib.ss_cosine_topk_stream_workspace_bytes(n, d, _dtype_code(corpus), b, k)
+            ws = workspace(dev, need)
+            st = lib.ss_cosine_topk_stream(
+                corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, _dtype_code(queries), k,
+                int(index_base), ws.data_ptr(), ws.numel(), keys.data_ptr() if keys is not None else None,
+                scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
+            _lib.check(st, "ss_cosine_topk_stream")
     if return_keys:
         return scores, idx, keys
     return scores, idx
