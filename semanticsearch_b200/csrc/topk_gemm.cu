@@ -117,26 +117,28 @@ __host__ __device__ constexpr uint32_t make_idesc(int ab_format, int m, int n) {
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// Sorted (descending) insertion into a register-resident top-KT list; strict '>' keeps the
-// earlier (lower-index) entry first among equal scores.
-template <int KT>
-__device__ __forceinline__ void list_insert_sorted(float (&v)[KT], int (&ix)[KT], float t, int c) {
-#pragma unroll
-  for (int j = KT - 1; j >= 1; --j) {
-    const bool up = t > v[j - 1];
-    const bool here = !up && (t > v[j]);
-    const float nv = up ? v[j - 1] : (here ? t : v[j]);
-    const int ni = up ? ix[j - 1] : (here ? c : ix[j]);
-    v[j] = nv;
-    ix[j] = ni;
+// Per-thread top-k list in shared memory, entry j of epilogue thread e at list[j * 128 + e]
+// (conflict-free across a warp).  Sorted descending; strict '>' keeps the earlier (lower-index)
+// entry first among equal scores.  Precondition: sc > current k-th best.  Returns the new k-th best.
+struct ScoreIdx {
+  float v;
+  int ix;
+};
+__device__ __noinline__ float epi_list_insert(ScoreIdx* list, int k, float sc, int c) {
+  int j = k - 1;
+  while (j > 0) {
+    const ScoreIdx up = list[(j - 1) * G_EPI_THREADS];
+    if (!(sc > up.v)) break;
+    list[j * G_EPI_THREADS] = up;
+    --j;
   }
-  if (t > v[0]) {
-    v[0] = t;
-    ix[0] = c;
-  }
+  ScoreIdx e;
+  e.v = sc;
+  e.ix = c;
+  list[j * G_EPI_THREADS] = e;
+  return list[(k - 1) * G_EPI_THREADS].v;
 }
 
-template <int KT>
 __global__ void __launch_bounds__(G_THREADS, 1)
 cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                         const GemmParams p, const uint32_t idesc) {
@@ -150,6 +152,7 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sinv = reinterpret_cast<float*>(tmem_ptr_s + 4);  // [2][G_BN] corpus inverse norms of the tile in flight
+  ScoreIdx* lists = reinterpret_cast<ScoreIdx*>(sinv + 2 * G_BN);  // [k][128] per-thread top-k lists
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.dim + G_BK - 1) / G_BK;
@@ -239,6 +242,7 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // query row inside the 128-row block
     const int et = (warp - 2) * 32 + lane;     // 0..127 among epilogue threads
+    ScoreIdx* my_list = lists + et;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -247,37 +251,83 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
       const int query = qb * G_BM + row;
       const float inv_q = query < p.n_queries ? p.inv_q[query] : 0.f;
-      float v[KT];
-      int ix[KT];
-#pragma unroll
-      for (int j = 0; j < KT; ++j) {
-        v[j] = -INFINITY;
-        ix[j] = -1;
+      for (int j = 0; j < p.k; ++j) {
+        ScoreIdx e;
+        e.v = -INFINITY;
+        e.ix = -1;
+        my_list[j * G_EPI_THREADS] = e;
       }
       float thr = -INFINITY;
+      // corpus inverse norms of the first tile (NaN for rows past the end: never selected);
+      // later tiles are prefetched one tile ahead so the global-load latency stays hidden
+      float inv_next[G_BN / G_EPI_THREADS];
+#pragma unroll
+      for (int h = 0; h < G_BN / G_EPI_THREADS; ++h) {
+        const long long gr = t0 * G_BN + h * G_EPI_THREADS + et;
+        inv_next[h] = gr < p.n_rows ? __ldg(p.inv_c + gr) : __int_as_float(0x7fc00000);
+      }
       for (long long t = t0; t < t1; ++t) {
-        // stage this tile's corpus inverse norms (NaN for rows past the end: never selected)
         float* inv_tile = sinv + acc * G_BN;
-        for (int c = et; c < G_BN; c += G_EPI_THREADS) {
-          const long long gr = t * G_BN + c;
-          inv_tile[c] = gr < p.n_rows ? p.inv_c[gr] : __int_as_float(0x7fc00000);
-        }
+#pragma unroll
+        for (int h = 0; h < G_BN / G_EPI_THREADS; ++h) inv_tile[h * G_EPI_THREADS + et] = inv_next[h];
         epi_bar_sync();
+        if (t + 1 < t1) {
+#pragma unroll
+          for (int h = 0; h < G_BN / G_EPI_THREADS; ++h) {
+            const long long gr = (t + 1) * G_BN + h * G_EPI_THREADS + et;
+            inv_next[h] = gr < p.n_rows ? __ldg(p.inv_c + gr) : __int_as_float(0x7fc00000);
+          }
+        }
         mbar_wait(&tmem_full[acc], acc_ph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * G_BN);
         const int col_base = static_cast<int>(t * G_BN);
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr, ra);
 #pragma unroll 1
-        for (int c0 = 0; c0 < G_BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + static_cast<uint32_t>(c0), r);
-          tmem_ld_wait();
+        for (int c0 = 0; c0 < G_BN; c0 += 64) {
+          tmem_ld_wait();                                   // ra = columns c0 .. c0+31
+          tmem_ld32(taddr + static_cast<uint32_t>(c0 + 32), rb);  // in flight while ra is processed
+          {
+            float m = -INFINITY;
+            float x[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sc = (__uint_as_float(r[j]) * inv_tile[c0 + j]) * inv_q;
-            if (sc > thr) {
-              list_insert_sorted<KT>(v, ix, sc, col_base + c0 + j);
-              thr = v[KT - 1];
+            for (int j = 0; j < 32; j += 4) {
+              const float4 iv = *reinterpret_cast<const float4*>(inv_tile + c0 + j);
+              x[j] = __uint_as_float(ra[j]) * iv.x;
+              x[j + 1] = __uint_as_float(ra[j + 1]) * iv.y;
+              x[j + 2] = __uint_as_float(ra[j + 2]) * iv.z;
+              x[j + 3] = __uint_as_float(ra[j + 3]) * iv.w;
+              m = fmaxf(fmaxf(fmaxf(m, x[j]), fmaxf(x[j + 1], x[j + 2])), x[j + 3]);
+            }
+            if (m * inv_q > thr) {  // rare once the list has warmed up
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float sc = x[j] * inv_q;
+                if (sc > thr) thr = epi_list_insert(my_list, p.k, sc, col_base + c0 + j);
+              }
+            }
+          }
+          tmem_ld_wait();                                   // rb = columns c0+32 .. c0+63
+          if (c0 + 64 < G_BN) tmem_ld32(taddr + static_cast<uint32_t>(c0 + 64), ra);
+          {
+            float m = -INFINITY;
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 iv = *reinterpret_cast<const float4*>(inv_tile + c0 + 32 + j);
+              x[j] = __uint_as_float(rb[j]) * iv.x;
+              x[j + 1] = __uint_as_float(rb[j + 1]) * iv.y;
+              x[j + 2] = __uint_as_float(rb[j + 2]) * iv.z;
+              x[j + 3] = __uint_as_float(rb[j + 3]) * iv.w;
+              m = fmaxf(fmaxf(fmaxf(m, x[j]), fmaxf(x[j + 1], x[j + 2])), x[j + 3]);
+            }
+            if (m * inv_q > thr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float sc = x[j] * inv_q;
+                if (sc > thr) thr = epi_list_insert(my_list, p.k, sc, col_base + c0 + 32 + j);
+              }
             }
           }
         }
@@ -291,9 +341,10 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
       if (query < p.n_queries) {
         uint64_t* out = p.partial + (static_cast<size_t>(chunk) * p.n_queries + query) * p.k;
-#pragma unroll
-        for (int j = 0; j < KT; ++j)
-          if (j < p.k) out[j] = ix[j] >= 0 ? make_key(v[j], p.index_base + static_cast<uint32_t>(ix[j])) : 0ull;
+        for (int j = 0; j < p.k; ++j) {
+          const ScoreIdx e = my_list[j * G_EPI_THREADS];
+          out[j] = e.ix >= 0 ? make_key(e.v, p.index_base + static_cast<uint32_t>(e.ix)) : 0ull;
+        }
       }
     }
   }
@@ -457,20 +508,15 @@ extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, 
   p.inv_q = inv_q;
   p.partial = partial;
   const uint32_t idesc = make_idesc(dtype == SS_BF16 ? 1 : 0, G_BM, G_BN);
-  const size_t smem = static_cast<size_t>(G_STAGES) * G_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4;
+  const size_t smem = static_cast<size_t>(G_STAGES) * G_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4 +
+                      static_cast<size_t>(k) * G_EPI_THREADS * sizeof(ScoreIdx);
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(sm_count(), p.n_units)));
-  auto launch = [&](auto kern) -> cudaError_t {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (err != cudaSuccess) return err;
+  e = cudaFuncSetAttribute(cosine_topk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e == cudaSuccess) {
     ProfileScope prof(st);
-    kern<<<grid, G_THREADS, smem, st>>>(tmap_q, tmap_c, p, idesc);
-    return cudaGetLastError();
-  };
-  if (k <= 1) e = launch(cosine_topk_gemm_kernel<1>);
-  else if (k <= 4) e = launch(cosine_topk_gemm_kernel<4>);
-  else if (k <= 8) e = launch(cosine_topk_gemm_kernel<8>);
-  else if (k <= 10) e = launch(cosine_topk_gemm_kernel<10>);
-  else e = launch(cosine_topk_gemm_kernel<16>);
+    cosine_topk_gemm_kernel<<<grid, G_THREADS, smem, st>>>(tmap_q, tmap_c, p, idesc);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) return cuda_fail(e, "cosine_topk_gemm launch");
   return ss_topk_merge(partial, g.n_chunks, n_queries, k, k, static_cast<int64_t>(n_queries) * k, k, out_keys, out_scores,
                        out_indices, stream);
