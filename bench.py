@@ -33,10 +33,12 @@ UNIT = "queries/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1, help="query batch size B (1 = HBM-bound headline)")
+    ap.add_argument("--batch", type=int, default=4096,
+                    help="query batch size B of the headline line (4096 = tensor-core path, 1 = HBM-bound streaming path)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the extra B=1 measurement reported under 'extra'")
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--k", type=int, default=10)
@@ -51,10 +53,11 @@ def peaks():
     if os.path.exists(path):
         try:
             d = json.load(open(path))
-            return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
+            return (float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)),
+                    float(d.get("bf16_tflops_sustained", 1400.0)), "measured")
         except Exception:
             pass
-    return 6650.0, 1590.0, "fallback"
+    return 6650.0, 1590.0, 1400.0, "fallback"
 
 
 # --------------------------------------------------------------------------------------------
@@ -212,11 +215,7 @@ def run_ours(args):
     lo, hi = shard_bounds(args.rows, world, rank)
     shard = make_shard(hi - lo, args.dim, 6 + rank, dev)
     corpus = ShardedCorpus(shard, lo)
-    gq = torch.Generator(device="cpu").manual_seed(7 if args.batch == 1 else 8)
-    q_host = torch.randn((args.batch, args.dim), generator=gq, dtype=torch.float32).to(torch.bfloat16).pin_memory()
-    q_dev = q_host.to(dev)
-    out_s_host = torch.empty((args.batch, args.k), dtype=torch.float32).pin_memory()
-    out_i_host = torch.empty((args.batch, args.k), dtype=torch.int64).pin_memory()
+    q_host = q_dev = out_s_host = out_i_host = None
     lib = _lib.load()
 
     def barrier():
@@ -257,46 +256,80 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), kern
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    total_ms, kern_ms = timed(step_resident, args.steps, profile=True)
-    clocks = sampler.stop() if sampler else None
-    for _ in range(3):
-        step_e2e()
-    e2e_ms, _ = timed(step_e2e, args.steps)
+    def measure(batch, steps, warmup):
+        """Device-resident and end-to-end timing of `steps` searches with a batch of `batch` queries."""
+        nonlocal q_host, q_dev, out_s_host, out_i_host
+        gq = torch.Generator(device="cpu").manual_seed(7 if batch == 1 else 8)
+        q_host = torch.randn((batch, args.dim), generator=gq, dtype=torch.float32).to(torch.bfloat16).pin_memory()
+        q_dev = q_host.to(dev)
+        out_s_host = torch.empty((batch, args.k), dtype=torch.float32).pin_memory()
+        out_i_host = torch.empty((batch, args.k), dtype=torch.int64).pin_memory()
+        for _ in range(max(warmup, 3)):
+            step_resident()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        total_ms, kern_ms = timed(step_resident, steps, profile=True)
+        clocks = sampler.stop() if sampler else None
+        for _ in range(3):
+            step_e2e()
+        e2e_ms, _ = timed(step_e2e, steps)
+        return total_ms, kern_ms, e2e_ms, clocks
 
-    # sanity: a planted winner must come back from whichever shard owns it
-    s, i = step_resident()
-    torch.cuda.synchronize()
-
-    if rank == 0:
-        hbm_peak, tf_peak, peak_src = peaks()
-        qps = args.batch * args.steps / (total_ms * 1e-3)
-        e2e_qps = args.batch * args.steps / (e2e_ms * 1e-3)
-        groups = (args.batch + 7) // 8 if args.batch > 1 else 1
-        # algorithmic bytes per launch of the dominant kernel: the local shard is read once per
-        # group of up to 8 queries (2*N*d bytes per query at B=1)
-        alg_bytes = (hi - lo) * args.dim * 2 * groups + args.batch * args.dim * 4 + args.batch * args.k * 8
+    def describe(batch, steps, total_ms, kern_ms, e2e_ms):
+        """value / e2e / roofline for one batch size (rank 0)."""
+        from semanticsearch_b200 import similarity
+        hbm_peak, tf_peak, tf_sustained, peak_src = peaks()
+        qps = batch * steps / (total_ms * 1e-3)
+        e2e_qps = batch * steps / (e2e_ms * 1e-3)
+        use_gemm = batch >= similarity.GEMM_MIN_BATCH and args.k <= 16
         k_avg = statistics.mean(kern_ms) if kern_ms else None
         roof = None
-        if k_avg:
+        if k_avg and use_gemm:
+            # algorithmic flops per launch: 2 * B * N_local * d (SURVEY.md section 8d, cfg 4b)
+            flops = 2.0 * batch * (hi - lo) * args.dim
+            achieved = flops / (k_avg * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                    "frac_of_sustained_peak": achieved / tf_sustained if tf_sustained else None, "traffic": None,
+                    "kernel": "cosine_topk_gemm_kernel (tcgen05)", "kernel_ms": k_avg,
+                    "kernel_share_of_step": k_avg * len(kern_ms) / total_ms, "peak_source": peak_src,
+                    "algorithmic_flops_per_launch": flops}
+        elif k_avg:
+            groups = (batch + 7) // 8 if batch > 1 else 1
+            # algorithmic bytes per launch: the local shard is read once per group of up to 8 queries
+            # (SURVEY.md section 8d: 2*N*d bytes per query at B=1)
+            alg_bytes = (hi - lo) * args.dim * 2 * groups + batch * args.dim * 2 + batch * args.k * 8
             achieved = alg_bytes / (k_avg * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": None, "kernel": "cosine_topk_stream_kernel", "kernel_ms": k_avg,
                     "kernel_share_of_step": k_avg * len(kern_ms) / total_ms, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes}
+        launches_per_step = (4 if use_gemm else 1) + (1 if world > 1 else 0)
+        return {"value": qps, "ms_per_step": total_ms / steps,
+                "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": batch * args.dim * 2,
+                        "d2h_bytes_per_step": batch * args.k * 12, "ms_per_step": e2e_ms / steps},
+                "gpu_launches": steps * launches_per_step, "roofline": roof}
+
+    total_ms, kern_ms, e2e_ms, clocks = measure(args.batch, args.steps, args.warmup)
+    main_res = describe(args.batch, args.steps, total_ms, kern_ms, e2e_ms) if rank == 0 else None
+    extra = None
+    if not args.no_secondary and args.batch != 1:
+        sec_steps = 50
+        t2, k2, e2, c2 = measure(1, sec_steps, 5)
+        if rank == 0:
+            extra = {"query_batch_1": dict(describe(1, sec_steps, t2, k2, e2), steps=sec_steps, clocks=c2,
+                                           note="same corpus, single query: the HBM-bound streaming kernel")}
+
+    if rank == 0:
         line = {
-            "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16 storage, f32 accumulate", "data": "synthetic", "config": workload_config(args),
-            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": args.batch * args.dim * 2,
-                    "d2h_bytes_per_step": args.batch * args.k * 12, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": args.steps * (1 + (1 if world > 1 else 0)),
-            "roofline": roof, "clocks": clocks,
+            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 storage, f32 accumulate", "data": "synthetic",
+            "config": workload_config(args), "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
+            "roofline": main_res["roofline"], "clocks": clocks,
         }
+        if extra:
+            line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_reference_qps(args)
         print(json.dumps(line))

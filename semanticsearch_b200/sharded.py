@@ -68,7 +68,8 @@ class ShardedCorpus:
         world = self.world_size
         if world == 1:
             return scores, idx
-        gathered = torch.empty((world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+        b, kk = keys.shape
+        gathered = torch.empty((world * b, kk), dtype=keys.dtype, device=keys.device)  # rank-major concatenation
         dist.all_gather_into_tensor(gathered, keys.contiguous(), group=self.group)
-        scores, idx, _ = self._merge(gathered, k)
+        scores, idx, _ = self._merge(gathered.view(world, b, kk), k)
         return scores, idx
