@@ -122,6 +122,21 @@ int ss_group_threshold_pass(const float* S, const int32_t* offsets, const int64_
                             int knn_mode, float* out_sharp, double* out_centrality, double* out_doc_stats,
                             int32_t* out_knn_idx, float* out_knn_val, void* stream);
 
+/* Similarity-distribution statistics of each document's strict upper triangle of S (layout of K3):
+ * values >= 1 - eps are dropped, then out_stats[d] = {count, min, max, mean, std, p10, p25, p50, p75,
+ * p80, p85, p90, p95} with numpy's float32 percentile arithmetic.  Device form of
+ * analyze_similarity_distribution (Method/semantic_common.py:250-270): count == 0 means every value was
+ * filtered and all fields hold max(sims) (:257-260); count == -1 means fewer than 2 rows (None). */
+int ss_similarity_distribution(const float* S, const int32_t* offsets, const int64_t* s_offsets, int n_docs, float eps,
+                               double* out_stats, void* stream);
+
+/* C99 rank transform of each document's S (layout of K3): global row+column rank
+ * (Method/Semantic_Splitter_Optimized.py:189-192) or the clipped mask_size x mask_size local rank
+ * (:171-186) when use_local_rank != 0.  workspace_rows: int32[total_rows] scratch. */
+int ss_c99_rank_matrix(const float* S, const int32_t* offsets, const int64_t* s_offsets, int n_docs, int total_rows,
+                       int max_doc_rows, int use_local_rank, int mask_size, int32_t* workspace_rows, float* out_R,
+                       void* stream);
+
 /* ---- K5: semantic-splitter passes over ragged documents ---------------------------------------
  * Documents are concatenated: rows = [total_rows x dim]; offsets = int32[n_docs+1] (device) CSR
  * row offsets.

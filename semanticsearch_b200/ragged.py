@@ -108,6 +108,40 @@ def group_threshold_pass(S: torch.Tensor, plan: RaggedPlan, tau: float = 0.15, k
     return {"sim_sharp": sharp, "centrality": cent, "doc_stats": stats, "knn_idx": kidx, "knn_val": kval}
 
 
+STAT_KEYS = ("min", "max", "mean", "std", "p10", "p25", "p50", "p75", "p80", "p85", "p90", "p95")
+
+
+def similarity_distribution(S: torch.Tensor, plan: RaggedPlan, eps: float = 1e-5) -> torch.Tensor:
+    """Per-document statistics of the strict upper triangle of S (Method/semantic_common.py:250-270).
+    Returns a float64 ``[D, 13]`` tensor: count, then the values of ``STAT_KEYS``."""
+    dev = _require_cuda(S)
+    if S.dtype != torch.float32 or not S.is_contiguous() or S.numel() < plan.total_s:
+        raise ValueError("S must be the packed float32 output of segmented_simmatrix")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        out = torch.empty((plan.n_docs, 13), dtype=torch.float64, device=dev)
+        st = lib.ss_similarity_distribution(S.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), plan.n_docs,
+                                            float(eps), out.data_ptr(), _stream_ptr(dev))
+        _lib.check(st, "ss_similarity_distribution")
+    return out
+
+
+def c99_rank_matrix(S: torch.Tensor, plan: RaggedPlan, use_local_rank: bool = False, mask_size: int = 11) -> torch.Tensor:
+    """C99 rank transform of every document's S (Method/Semantic_Splitter_Optimized.py:171-192), packed like S."""
+    dev = _require_cuda(S)
+    if S.dtype != torch.float32 or not S.is_contiguous() or S.numel() < plan.total_s:
+        raise ValueError("S must be the packed float32 output of segmented_simmatrix")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        R = torch.empty(plan.total_s, dtype=torch.float32, device=dev)
+        ws = torch.empty(max(plan.total_rows, 1), dtype=torch.int32, device=dev)
+        st = lib.ss_c99_rank_matrix(S.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), plan.n_docs,
+                                    plan.total_rows, max(plan.max_rows, 1), int(bool(use_local_rank)), int(mask_size),
+                                    ws.data_ptr(), R.data_ptr(), _stream_ptr(dev))
+        _lib.check(st, "ss_c99_rank_matrix")
+    return R
+
+
 def adjacent_cosine(E: torch.Tensor) -> torch.Tensor:
     """``adj[r] = cos(E[r], E[r+1])`` for the whole concatenated matrix
     (Method/Semantic_Splitter_Optimized.py:140-152,412); the last row gets 0."""

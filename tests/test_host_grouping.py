@@ -1,0 +1,65 @@
+"""CPU tests of the grouping drop-in's host stage: fed with the reference's own intermediate
+arrays (tests/golden/grouping.npz, captured from the unmodified reference), the re-implemented
+sequential clustering must reproduce the reference's clusters and metadata exactly."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import grouping_oracle as go
+from semanticsearch_b200.Method import Semantic_Grouping_Optimized as G
+
+
+def _device_pass_from_golden(g, meta, name):
+    sc = meta[f"{name}_scalars"]
+    sharp = g[f"{name}_sim_sharp"]
+    n = sharp.shape[0]
+    idx, val = go.knn_lists_ref(sharp, sc["k_eff_all"])
+    kidx = np.full((n, 33), -1, np.int32)
+    kval = np.zeros((n, 33), np.float32)
+    kidx[:, :idx.shape[1]] = idx
+    kval[:, :val.shape[1]] = val
+    thr = go.thresholds_ref(sharp)
+    return G.DevicePass(sim_matrix=g[f"{name}_S"], sim_sharp=sharp, centrality=g[f"{name}_centrality"], mu=sc["mu"],
+                        sigma=sc["sigma"], q80=thr["edge_floor"], q65=thr["tau_merge"], q60=thr["global_merge_thr"],
+                        reassign_delta=thr["reassign_delta"], n_positive=thr["count"], k_all=sc["k_eff_all"],
+                        knn_idx=kidx, knn_val=kval)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "tiny", "seven"])
+def test_host_stage_reproduces_reference_clusters(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "grouping.npz"))
+    meta = json.loads(str(g["meta_json"]))
+    dp = _device_pass_from_golden(g, meta, name)
+    merged, method, W = G.cluster_from_device_pass(dp, W_override=g[f"{name}_W_all"])
+    assert method == meta[f"{name}_scalars"]["method_used"]
+    n = dp.sim_sharp.shape[0]
+    sentences = [f"s{i}" for i in range(n)]
+    chunks = G._emit(f"doc_{name}", "whole", sentences, merged, method, dp, collect_metadata=True)
+    want = meta[f"{name}_chunks"]
+    assert [c[0] for c in chunks] == [w[0] for w in want]
+    for (cid, _text, mjson), (wid, wjson) in zip(chunks, want):
+        assert json.loads(mjson) == json.loads(wjson), cid
+
+
+def test_knn_graph_from_lists_matches_oracle(golden_dir):
+    from semanticsearch_b200.ragged import knn_graph_from_lists
+    g = np.load(os.path.join(golden_dir, "grouping.npz"))
+    meta = json.loads(str(g["meta_json"]))
+    for name in ("a", "b", "c", "seven"):
+        sharp = g[f"{name}_sim_sharp"]
+        sc = meta[f"{name}_scalars"]
+        idx, val = go.knn_lists_ref(sharp, sc["k_eff_all"])
+        W = knn_graph_from_lists(idx, val, sc["eff_edge_floor"])
+        np.testing.assert_array_equal(W, go.knn_graph_ref(sharp, sc["k_eff_all"], sc["eff_edge_floor"]))
+
+
+def test_sentinels_without_gpu():
+    from semanticsearch_b200.Tool import Sentence_Segmenter as seg
+    seg.set_sentence_splitter(lambda t: [s for s in t.split("|") if s])
+    try:
+        assert G.semantic_grouping_main("", "d0", "m", silent=True) == []
+        assert G.semantic_grouping_main("only one sentence here", "d1", "m", silent=True) == [("d1_single", "only one sentence here", None)]
+    finally:
+        seg.set_sentence_splitter(None)
