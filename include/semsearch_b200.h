@@ -69,6 +69,17 @@ int ss_cosine_topk_stream(const void* corpus, int64_t n_rows, int dim, int corpu
                           uint64_t* out_keys, float* out_scores, int64_t* out_indices,
                           void* stream);
 
+/* Full score matrix and full ordering (the ranker needs every chunk's score and rank, not only the
+ * top k): ss_cosine_scores writes out_all_scores[q][row] = cos(query q, corpus row) with the K1
+ * streaming kernel (Tool/rank_chunks_optimized.py:215-216); ss_rank_order is np.argsort(-scores) and
+ * the 1-based rank lookup of :225-235 (out_order[q][r] = row at rank r, out_rank1[q][row] = rank + 1;
+ * equal scores -> lower row first).  Workspace for ss_cosine_scores: the ss_cosine_topk_stream size with k = 1. */
+int ss_cosine_scores(const void* corpus, int64_t n_rows, int dim, int corpus_dtype, const void* queries, int n_queries,
+                     int query_dtype, void* workspace, size_t workspace_bytes, float* out_all_scores, void* stream);
+size_t ss_rank_order_workspace_bytes(int n_queries, int64_t n);
+int ss_rank_order(const float* scores, int n_queries, int64_t n, void* workspace, size_t workspace_bytes,
+                  int32_t* out_order, int32_t* out_rank1, void* stream);
+
 /* ---- K2: tensor-core cosine + fused top-k, large query batches ---------------------------------
  * Same contract as ss_cosine_topk_stream for bf16/fp16 corpora and queries of the same dtype, k <= 16,
  * dim % 8 == 0: D = Q C^T on tcgen05 tensor cores (TMA-fed shared-memory operands, fp32

@@ -44,6 +44,7 @@ struct StreamParams {
   uint64_t* out_keys;     // final outputs, each [n_queries][k] or nullptr
   float* out_scores;
   long long* out_indices;
+  float* all_scores;      // optional [n_queries][n_rows] full score matrix (ranker drop-in), else nullptr
 };
 
 // ------------------------------------------------------------------------------------------
@@ -337,6 +338,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) cosine_topk_stream_kernel(c
         // sklearn's zero rule: a zero row is divided by 1 and scores 0.
         const float inv = ssq > 0.f ? 1.0f / sqrtf(ssq) : 1.0f;
         const bool row_ok = (r0 + v_row) < rows;
+        if (p.all_scores != nullptr && v_live && row_ok && (lane & ((1 << SH) - 1)) == 0)
+          p.all_scores[static_cast<size_t>(q0 + v_q) * p.n_rows + (row0 + r0 + v_row)] = mine * inv;
         const uint64_t key = make_key(mine * inv, p.index_base + static_cast<uint32_t>(row0 + r0 + v_row));
         const bool pass = v_live && row_ok && key > my_thr[v_live ? v_q : 0];
         uint32_t ballot = __ballot_sync(0xffffffffu, pass);
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(kGenericThreads, 1) cosine_topk_generic_kernel
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
       const float d = warp_sum(dot[b]);
+      if (p.all_scores != nullptr && b < nq && lane == 0) p.all_scores[static_cast<size_t>(q0 + b) * p.n_rows + r] = d * inv;
       const uint64_t key = make_key(d * inv, grow);
       if (b < nq && key > thr[b]) thr[b] = list_insert(my_lists + b * p.kpad, p.kpad, key, lane);
     }
@@ -533,10 +537,9 @@ extern "C" size_t ss_cosine_topk_stream_workspace_bytes(int64_t n_rows, int dim,
   return tickets + partial + 256;
 }
 
-extern "C" int ss_cosine_topk_stream(const void* corpus, int64_t n_rows, int dim, int corpus_dtype, const void* queries,
-                                     int n_queries, int query_dtype, int k, uint32_t index_base, void* workspace,
-                                     size_t workspace_bytes, uint64_t* out_keys, float* out_scores, int64_t* out_indices,
-                                     void* stream) {
+static int run_stream(const void* corpus, int64_t n_rows, int dim, int corpus_dtype, const void* queries, int n_queries,
+                      int query_dtype, int k, uint32_t index_base, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
+                      float* out_scores, int64_t* out_indices, float* all_scores, void* stream) {
   if (!corpus || !queries || !workspace) return fail(SS_ERR_INVALID_ARG, "ss_cosine_topk_stream: null pointer");
   if (n_rows <= 0 || dim <= 0 || n_queries <= 0 || k <= 0)
     return fail(SS_ERR_INVALID_ARG, "ss_cosine_topk_stream: n_rows, dim, n_queries and k must be positive");
@@ -577,6 +580,7 @@ extern "C" int ss_cosine_topk_stream(const void* corpus, int64_t n_rows, int dim
   p.out_keys = out_keys;
   p.out_scores = out_scores;
   p.out_indices = reinterpret_cast<long long*>(out_indices);
+  p.all_scores = all_scores;
   const int chunks = static_cast<int>(static_cast<size_t>(dim) * dtype_size(corpus_dtype) / 16);
   cudaError_t e;
   {
@@ -589,4 +593,19 @@ extern "C" int ss_cosine_topk_stream(const void* corpus, int64_t n_rows, int dim
   }
   if (e != cudaSuccess) return cuda_fail(e, "cosine_topk_stream launch");
   return SS_OK;
+}
+
+extern "C" int ss_cosine_topk_stream(const void* corpus, int64_t n_rows, int dim, int corpus_dtype, const void* queries,
+                                     int n_queries, int query_dtype, int k, uint32_t index_base, void* workspace,
+                                     size_t workspace_bytes, uint64_t* out_keys, float* out_scores, int64_t* out_indices,
+                                     void* stream) {
+  return run_stream(corpus, n_rows, dim, corpus_dtype, queries, n_queries, query_dtype, k, index_base, workspace, workspace_bytes,
+                    out_keys, out_scores, out_indices, nullptr, stream);
+}
+
+extern "C" int ss_cosine_scores(const void* corpus, int64_t n_rows, int dim, int corpus_dtype, const void* queries, int n_queries,
+                                int query_dtype, void* workspace, size_t workspace_bytes, float* out_all_scores, void* stream) {
+  if (!out_all_scores) return fail(SS_ERR_INVALID_ARG, "ss_cosine_scores: null output");
+  return run_stream(corpus, n_rows, dim, corpus_dtype, queries, n_queries, query_dtype, 1, 0, workspace, workspace_bytes, nullptr,
+                    nullptr, nullptr, out_all_scores, stream);
 }

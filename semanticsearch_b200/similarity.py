@@ -108,6 +108,46 @@ def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_ba
     return scores, idx
 
 
+def cosine_scores(corpus: torch.Tensor, queries: torch.Tensor) -> torch.Tensor:
+    """Full ``[B, N]`` float32 cosine matrix — ``cosine_similarity(Q, C)`` of
+    Tool/rank_chunks_optimized.py:215-216 for callers that need every score (RRF ranks)."""
+    dev = _require_cuda(corpus, queries)
+    if corpus.dim() != 2 or queries.dim() != 2 or corpus.shape[1] != queries.shape[1]:
+        raise ValueError(f"shape mismatch: corpus {tuple(corpus.shape)} vs queries {tuple(queries.shape)}")
+    if not corpus.is_contiguous() or not queries.is_contiguous():
+        raise ValueError("corpus and queries must be contiguous row-major tensors")
+    n, d = corpus.shape
+    b = queries.shape[0]
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        need = lib.ss_cosine_topk_stream_workspace_bytes(n, d, _dtype_code(corpus), b, 1)
+        ws = workspace(dev, need)
+        out = torch.empty((b, n), dtype=torch.float32, device=dev)
+        st = lib.ss_cosine_scores(corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, _dtype_code(queries),
+                                  ws.data_ptr(), ws.numel(), out.data_ptr(), _stream_ptr(dev))
+        _lib.check(st, "ss_cosine_scores")
+    return out
+
+
+def rank_order(scores: torch.Tensor):
+    """``(order, rank1)`` for each row of ``scores [B, N]``: ``order`` = ``np.argsort(-scores)``
+    (ties: lower index first), ``rank1[b, i]`` = 1-based rank of element i
+    (Tool/rank_chunks_optimized.py:225-235)."""
+    dev = _require_cuda(scores)
+    if scores.dim() != 2 or scores.dtype != torch.float32 or not scores.is_contiguous():
+        raise ValueError("scores must be a contiguous float32 [B, N] tensor")
+    b, n = scores.shape
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws = workspace(dev, lib.ss_rank_order_workspace_bytes(b, n), "sort")
+        order = torch.empty((b, n), dtype=torch.int32, device=dev)
+        rank1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+        st = lib.ss_rank_order(scores.data_ptr(), b, n, ws.data_ptr(), ws.numel(), order.data_ptr(), rank1.data_ptr(),
+                               _stream_ptr(dev))
+        _lib.check(st, "ss_rank_order")
+    return order, rank1
+
+
 def topk_merge(keys: torch.Tensor, k_out: Optional[int] = None):
     """Merge ``keys[P, B, k]`` (P best-first lists per query) into the global top ``k_out``.
 

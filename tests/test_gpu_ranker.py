@@ -1,0 +1,117 @@
+"""GPU tests for the full-score / full-order kernels and the ranker drop-in
+(semanticsearch_b200.Tool.rank_chunks_optimized)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import rank_oracle as ro
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("b,n", [(1, 1), (1, 2), (3, 100), (2, 2048), (2, 2049), (1, 5000), (1, 70001), (4, 4096)])
+def test_rank_order_matches_stable_argsort(b, n):
+    from semanticsearch_b200 import similarity
+    rng = np.random.default_rng(b * 100003 + n)
+    s = rng.standard_normal((b, n)).astype(np.float32)
+    s[:, n // 3] = s[:, 0]            # ties
+    if n > 10:
+        s[0, 5:9] = 0.25
+    order, rank1 = similarity.rank_order(torch.from_numpy(s).cuda())
+    order, rank1 = order.cpu().numpy(), rank1.cpu().numpy()
+    for q in range(b):
+        want = ro.rank_order_ref(s[q])
+        np.testing.assert_array_equal(order[q], want)
+        lookup = np.zeros(n, dtype=np.int64)
+        lookup[want] = np.arange(1, n + 1)
+        np.testing.assert_array_equal(rank1[q], lookup)
+
+
+@pytest.mark.parametrize("dtype,d", [(torch.float32, 384), (torch.bfloat16, 768), (torch.float32, 50)])
+def test_cosine_scores_full_matrix(dtype, d):
+    from semanticsearch_b200 import similarity
+    rng = np.random.default_rng(d)
+    C = rng.standard_normal((7001, d)).astype(np.float32)
+    Q = rng.standard_normal((5, d)).astype(np.float32)
+    C[11] = 0.0
+    Ct, Qt = torch.from_numpy(C).cuda().to(dtype), torch.from_numpy(Q).cuda().to(dtype)
+    got = similarity.cosine_scores(Ct, Qt).cpu().numpy()
+    want = ro.cosine_similarity_ref(Qt.float().cpu().numpy(), Ct.float().cpu().numpy())
+    np.testing.assert_allclose(got, want, atol=1e-5, rtol=0)
+    assert np.all(got[:, 11] == 0.0)
+
+
+def test_cosine_similarity_dropin_matches_reference_fixture(golden_dir):
+    from semanticsearch_b200.Tool import rank_chunks_optimized as R
+    g = np.load(os.path.join(golden_dir, "rank_cosine.npz"))
+    for b in range(g["Q"].shape[0]):
+        got = R.cosine_similarity(g["Q"][b].reshape(1, -1), g["C"])[0]   # the call at rank_chunks_optimized.py:216
+        assert got.dtype == np.float32
+        np.testing.assert_allclose(got, g["scores"][b], atol=1e-5, rtol=0)
+
+
+def test_optimized_ranker_dropin(golden_dir):
+    from semanticsearch_b200.Tool import Sentence_Embedding as emb
+    from semanticsearch_b200.Tool import rank_chunks_optimized as R
+    g = np.load(os.path.join(golden_dir, "rank_cosine.npz"))
+    C, Q = g["C"], g["Q"]
+    texts = [f"chunk {i:04d} alpha" if i % 2 else f"chunk {i:04d} beta" for i in range(len(C))]
+    table = {t: v for t, v in zip(texts, C)}
+    table["alpha query"] = Q[0]
+    emb.set_embedding_backend(lambda text_list, model_name, batch_size=32, device_preference=None:
+                              np.stack([table[t] for t in text_list]).astype(np.float32))
+    try:
+        ranker = R.OptimizedRanker(model_name="m", device_preference="cuda", cache_size=100000)
+        df = pd.DataFrame({"chunk_id": [f"c{i}" for i in range(len(C))], "chunk_text": texts})
+        ranked = ranker.rank_single_query_optimized("alpha query", df)
+        assert list(ranked.columns) == ["chunk_id", "chunk_text", "cosine_score", "bm25_score", "rrf_score"]
+        by_id = ranked.set_index("chunk_id").loc[df["chunk_id"]]
+        # the cosine column equals the reference ranker's (rank_chunks_optimized.py:201-250 through the shim)
+        np.testing.assert_allclose(by_id["cosine_score"].to_numpy(), g["ranker_cosine_q0"], atol=1e-5, rtol=0)
+        cos = by_id["cosine_score"].to_numpy(dtype=np.float32)
+        bm = by_id["bm25_score"].to_numpy()
+        assert np.all(bm >= 0) and bm[1] > 0 and bm[0] == 0
+        cr = np.empty(len(C)); cr[ro.rank_order_ref(cos)] = np.arange(1, len(C) + 1)
+        br = np.empty(len(C)); br[ro.rank_order_ref(bm.astype(np.float32))] = np.arange(1, len(C) + 1)
+        np.testing.assert_allclose(by_id["rrf_score"].to_numpy(), 1.0 / (60 + cr) + 1.0 / (60 + br), rtol=1e-12)
+        assert np.all(np.diff(ranked["rrf_score"].to_numpy()) <= 0)
+        s, i = ranker.top_k("alpha query", texts, 10)
+        assert list(i) == list(ro.rank_order_ref(cos)[:10])
+        with pytest.raises(ValueError):
+            ranker.rank_single_query_optimized("alpha query", df.rename(columns={"chunk_text": "x"}))
+        legacy = R.rank_by_cosine_similarity("alpha query", df, model_name="m", device_preference="cuda")
+        assert legacy["cosine_score"].is_monotonic_decreasing
+    finally:
+        emb.set_embedding_backend(None)
+
+
+def test_rank_and_filter_end_to_end(tmp_path):
+    from semanticsearch_b200.Tool import Sentence_Embedding as emb
+    from semanticsearch_b200.Tool import rank_chunks_optimized as R
+    rng = np.random.default_rng(0)
+    rows, table = [], {}
+    for q in range(3):
+        table[f"query text {q}"] = rng.standard_normal(32).astype(np.float32)
+        for c in range(40):
+            t = f"q{q} chunk {c} words {c % 5}"
+            table[t] = rng.standard_normal(32).astype(np.float32)
+            rows.append({"query_id": f"Q{q}", "chunk_id": f"Q{q}_c{c}", "chunk_text": t})
+    chunks = tmp_path / "chunks.tsv"
+    pd.DataFrame(rows).to_csv(chunks, sep="\t", index=False)
+    orig = tmp_path / "orig.tsv"
+    pd.DataFrame({"query_id": [f"Q{q}" for q in range(3)], "query_text": [f"query text {q}" for q in range(3)]}).to_csv(orig, sep="\t", index=False)
+    emb.set_embedding_backend(lambda text_list, model_name, batch_size=32, device_preference=None:
+                              np.stack([table[t] for t in text_list]).astype(np.float32))
+    try:
+        out = R.rank_and_filter_chunks_optimized(str(chunks), tmp_path, str(orig), model_name="m")
+        assert out.endswith("chunks_rrf_filtered.tsv")
+        res = pd.read_csv(out, sep="\t")
+        assert list(res.columns) == ["query_id", "chunk_text", "label"]
+        assert set(res["label"]) == {0, 1} and res["query_id"].nunique() == 3
+        assert 3 * 14 <= len(res) <= 3 * 20   # ~ top 20% + bottom 20% of 40 chunks per query
+        assert R.rank_and_filter_chunks_optimized(str(tmp_path / "missing.tsv"), tmp_path, str(orig)) == ""
+    finally:
+        emb.set_embedding_backend(None)
