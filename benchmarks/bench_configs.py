@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Secondary benchmarks for BASELINE.json configs 1, 2, 3 and 5 (bench.py covers config 4).
+
+    python benchmarks/bench_configs.py --config 1|2|3|5 [--steps K] [--docs D]
+
+Prints one JSON line per config: throughput, CUDA-event kernel times, fraction of the measured HBM
+roofline on the algorithmic bytes of SURVEY.md section 8(d), and the reference's own CPU expression
+timed on a bounded sample of the same synthetic workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from semanticsearch_b200 import ragged, similarity  # noqa: E402
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def cuda_time(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def topic_rows(sizes, d, seed, device):
+    """SURVEY.md 8(d) cfg 2/3 generator: one topic centroid per ~12 sentences + 0.7 * noise."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sizes_t = torch.as_tensor(sizes, device=device)
+    total = int(sizes_t.sum())
+    doc_of = torch.repeat_interleave(torch.arange(len(sizes), device=device), sizes_t)
+    start = torch.cumsum(sizes_t, 0) - sizes_t
+    local = torch.arange(total, device=device) - start[doc_of]
+    topics_per_doc = (sizes_t + 11) // 12
+    topic_base = torch.cumsum(topics_per_doc, 0) - topics_per_doc
+    topic = topic_base[doc_of] + local // 12
+    cent = torch.randn((int(topics_per_doc.sum()), d), generator=g, device=device)
+    out = torch.empty((total, d), dtype=torch.float32, device=device)
+    step = 1 << 20
+    for a in range(0, total, step):
+        b = min(total, a + step)
+        out[a:b] = cent[topic[a:b]] + 0.7 * torch.randn((b - a, d), generator=g, device=device)
+    return out
+
+
+def config1(args):
+    C = torch.from_numpy(np.random.default_rng(1).standard_normal((10000, 384)).astype(np.float32)).cuda()
+    Q = torch.from_numpy(np.random.default_rng(2).standard_normal((100, 384)).astype(np.float32)).cuda()
+    ms = cuda_time(lambda: similarity.cosine_topk(C, Q, 10), args.steps)
+    from sklearn.metrics.pairwise import cosine_similarity
+    Ch, Qh = C.cpu().numpy(), Q.cpu().numpy()
+    t0 = time.perf_counter()
+    for b in range(100):
+        np.argsort(-cosine_similarity(Qh[b].reshape(1, -1), Ch)[0])[:10]
+    cpu_s = time.perf_counter() - t0
+    return {"config": "cfg1: 100 queries x 10k chunks x 384 fp32, top-10", "metric": "queries/s", "value": 100 / (ms * 1e-3),
+            "ms": ms, "bound": "launch/L2 (15.5 MB working set)", "cpu_baseline": {"value": 100 / cpu_s, "unit": "queries/s",
+            "cores": len(os.sched_getaffinity(0)), "kind": "port", "sample": "full config, rank_chunks_optimized.py:215-216,225 per query"}}
+
+
+def config2(args):
+    rng = np.random.default_rng(3)
+    D = args.docs or 10000
+    sizes = rng.integers(16, 513, size=D)
+    E = topic_rows(sizes, 768, 4, "cuda")
+    plan = ragged.make_plan(sizes, "cuda")
+    S = torch.empty(plan.total_s, dtype=torch.float32, device="cuda")
+    ms_sim = cuda_time(lambda: ragged.segmented_simmatrix(E, plan, out=S), args.steps)
+    ms_grp = cuda_time(lambda: ragged.group_threshold_pass(S, plan), max(1, args.steps // 2), warmup=1)
+    peak, src = hbm_peak()
+    alg = 4 * 768 * plan.total_rows + 4 * plan.total_s
+    # CPU: the reference's arithmetic for the same pass, on a sample of documents
+    from oracle import grouping_oracle as go, simmatrix_oracle as so
+    sample = list(range(0, D, max(1, D // 40)))[:40]
+    Eh = [E[plan.offsets[d]:plan.offsets[d + 1]].cpu().numpy() for d in sample]
+    t0 = time.perf_counter()
+    for e in Eh:
+        go.grouping_pass_ref(so.similarity_matrix_ref(e))
+    cpu_s = (time.perf_counter() - t0) / len(sample)
+    return {"config": f"cfg2: {D} docs, n~U[16,512], 768-d fp32: S = En En^T + grouping threshold pass", "metric": "docs/s",
+            "value": D / ((ms_sim + ms_grp) * 1e-3), "ms_simmatrix": ms_sim, "ms_group_pass": ms_grp,
+            "rows": plan.total_rows, "sum_n2": plan.total_s,
+            "roofline": {"bound": "hbm", "kernel": "segmented_simmatrix_kernel", "achieved": alg / (ms_sim * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (ms_sim * 1e-3) / 1e9 / peak, "peak_source": src,
+                         "algorithmic_bytes_per_launch": alg, "fp32_tflops": 2 * 768 * plan.total_s / (ms_sim * 1e-3) / 1e12},
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "docs/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                             "sample": f"{len(sample)} documents: numpy S (semantic_common.py:158-191) + sharpen/quantile/kNN "
+                                       f"(Semantic_Grouping_Optimized.py:100-115,270-283,343-360)"}}
+
+
+def config3(args):
+    rng = np.random.default_rng(5)
+    D = args.docs or 50000
+    sizes = rng.integers(16, 513, size=D)
+    E = topic_rows(sizes, 384, 5, "cuda")
+    plan = ragged.make_plan(sizes, "cuda")
+    adj_holder = {}
+
+    def step():
+        adj = ragged.adjacent_cosine(E)
+        adj_holder["out"] = ragged.segmented_percentile(adj, plan, 95.0, want_stats=False)
+
+    ms_adj = cuda_time(lambda: ragged.adjacent_cosine(E), args.steps)
+    ms_all = cuda_time(step, args.steps)
+    peak, src = hbm_peak()
+    alg = 4 * 384 * plan.total_rows + 4 * plan.total_rows + 8 * D
+    from oracle import splitter_oracle as spo
+    sample = list(range(0, D, max(1, D // 200)))[:200]
+    Eh = [E[plan.offsets[d]:plan.offsets[d + 1]].cpu().numpy() for d in sample]
+    t0 = time.perf_counter()
+    for e in Eh:
+        spo.p95_breakpoints_ref(spo.adjacent_sims_ref(e))
+    cpu_s = (time.perf_counter() - t0) / len(sample)
+    return {"config": f"cfg3: adjacent-sentence distance + P95 breakpoints, {D}-doc batch of n~U[16,512] x 384 fp32 "
+                      f"(1M docs = {1_000_000 // D} such batches)", "metric": "docs/s", "value": D / (ms_all * 1e-3),
+            "ms_adjacent": ms_adj, "ms_total": ms_all, "rows": plan.total_rows,
+            "roofline": {"bound": "hbm", "kernel": "adjacent_cosine_kernel", "achieved": alg / (ms_adj * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / (ms_adj * 1e-3) / 1e9 / peak, "peak_source": src,
+                         "algorithmic_bytes_per_launch": alg},
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "docs/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                             "sample": f"{len(sample)} documents: _embed normalise + adjacent dot loop (Semantic_Splitter_Optimized.py:"
+                                       f"140-152,412) + np.percentile(1-adj, 95)"}}
+
+
+def config5(args):
+    n, d, b, k = args.rows or 12_500_000, 384, 16, 100
+    g = torch.Generator(device="cuda").manual_seed(9)
+    C = torch.empty((n, d), dtype=torch.float16, device="cuda")
+    for a in range(0, n, 1 << 21):
+        e = min(n, a + (1 << 21))
+        C[a:e] = torch.randn((e - a, d), generator=g, device="cuda").half()
+    Q = torch.randn((b, d), generator=torch.Generator(device="cuda").manual_seed(10), device="cuda").half()
+    ms = cuda_time(lambda: similarity.cosine_topk(C, Q, k), args.steps)
+    peak, src = hbm_peak()
+    alg = 2 * n * d
+    return {"config": f"cfg5 (one of 8 shards): top-100 over {n} x 384 fp16, 16-query batch", "metric": "queries/s per shard-GPU",
+            "value": b / (ms * 1e-3), "ms": ms,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": src, "algorithmic_bytes_per_launch": alg}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, required=True, choices=[1, 2, 3, 5])
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--docs", type=int, default=0)
+    ap.add_argument("--rows", type=int, default=0)
+    args = ap.parse_args()
+    res = {1: config1, 2: config2, 3: config3, 5: config5}[args.config](args)
+    res["data"] = "synthetic"
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
