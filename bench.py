@@ -282,7 +282,8 @@ def run_ours(args):
         hbm_peak, tf_peak, tf_sustained, peak_src = peaks()
         qps = batch * steps / (total_ms * 1e-3)
         e2e_qps = batch * steps / (e2e_ms * 1e-3)
-        use_gemm = batch >= similarity.GEMM_MIN_BATCH and args.k <= 16
+        algo = similarity.choose_algo(shard, q_dev, args.k)
+        use_gemm = algo == "gemm"
         k_avg = statistics.mean(kern_ms) if kern_ms else None
         roof = None
         if k_avg and use_gemm:
@@ -295,16 +296,18 @@ def run_ours(args):
                     "kernel_share_of_step": k_avg * len(kern_ms) / total_ms, "peak_source": peak_src,
                     "algorithmic_flops_per_launch": flops}
         elif k_avg:
-            groups = (batch + 7) // 8 if batch > 1 else 1
-            # algorithmic bytes per launch: the local shard is read once per group of up to 8 queries
-            # (2*N*d bytes per query at B=1)
+            # algorithmic bytes per launch: the local shard is read once per query group — up to 8 queries
+            # in K1, up to 64 in K7 (2*N*d bytes per query at B=1)
+            groups = (batch + 63) // 64 if algo == "tcstream" else ((batch + 7) // 8 if batch > 1 else 1)
             alg_bytes = (hi - lo) * args.dim * 2 * groups + batch * args.dim * 2 + batch * args.k * 8
             achieved = alg_bytes / (k_avg * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "kernel": "cosine_topk_stream_kernel", "kernel_ms": k_avg,
+                    "traffic": None,
+                    "kernel": "cosine_topk_tcstream_kernel (tcgen05)" if algo == "tcstream" else "cosine_topk_stream_kernel",
+                    "kernel_ms": k_avg,
                     "kernel_share_of_step": k_avg * len(kern_ms) / total_ms, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes}
-        launches_per_step = (4 if use_gemm else 1) + (1 if world > 1 else 0)
+        launches_per_step = {"gemm": 4, "tcstream": 2, "stream": 1}[algo] + (1 if world > 1 else 0)
         return {"value": qps, "ms_per_step": total_ms / steps,
                 "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": batch * args.dim * 2,
                         "d2h_bytes_per_step": batch * args.k * 12, "ms_per_step": e2e_ms / steps},

@@ -92,6 +92,20 @@ int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, int dtype,
                         void* workspace, size_t workspace_bytes,
                         uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
 
+/* ---- K7: tensor-core streaming cosine + fused top-k, medium query batches -----------------------
+ * Same contract as ss_cosine_topk_gemm (bf16/fp16, one dtype for corpus and queries, dim % 8 == 0)
+ * with k <= 1024: the corpus tile is the MMA M operand and up to 64 queries stay resident in shared
+ * memory as the N operand, corpus norms are accumulated from the shared-memory tiles the MMA reads, so
+ * the corpus streams from HBM exactly once per group of 64 queries; survivors of a per-query
+ * threshold go to shared-memory candidate pools that are bitonic-sorted back to k when nearly full.
+ * Replaces Tool/rank_chunks_optimized.py:215-216,225-235 for batches too large for K1's FMA budget
+ * and too small for K2's 128-query tiles (BASELINE.json config 5: 16 queries, top-100, fp16). */
+size_t ss_cosine_topk_tcstream_workspace_bytes(int64_t n_rows, int dim, int n_queries, int k);
+int ss_cosine_topk_tcstream(const void* corpus, int64_t n_rows, int dim, int dtype,
+                            const void* queries, int n_queries, int k, uint32_t index_base,
+                            void* workspace, size_t workspace_bytes,
+                            uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
+
 /* ---- K6: k-way merge of best-first key lists ------------------------------------------------
  * Merges n_lists sorted lists per query (per-CTA partials, or per-GPU results after an NCCL
  * all-gather) into the global top k_out.  key(q, p, j) = keys_in[q*query_stride + p*list_stride + j].

@@ -49,13 +49,36 @@ def workspace(dev: torch.device, nbytes: int, tag: str = "default") -> torch.Ten
     return buf
 
 
-GEMM_MIN_BATCH = 16  # from this many queries on, bf16/fp16 work goes to the tensor-core kernel
+# Dispatch thresholds for 16-bit corpora (measured on B200, profiles/):
+#   queries <  TC_MIN_BATCH              -> K1 CUDA-core streaming kernel (HBM-bound up to a few queries)
+#   TC_MIN_BATCH <= queries < GEMM_MIN_BATCH, or k > 16 -> K7 tensor-core streaming kernel (HBM-bound)
+#   queries >= GEMM_MIN_BATCH and k <= 16 -> K2 tensor-core GEMM kernel (tensor-bound)
+TC_MIN_BATCH = 2
+GEMM_MIN_BATCH = 96
+_ALGOS = ("auto", "stream", "gemm", "tcstream")
+
+
+def _lowp_eligible(corpus: torch.Tensor, queries: torch.Tensor) -> bool:
+    return (corpus.dtype in (torch.bfloat16, torch.float16) and queries.dtype == corpus.dtype
+            and corpus.shape[1] % 8 == 0 and corpus.data_ptr() % 16 == 0 and queries.data_ptr() % 16 == 0
+            and corpus.shape[0] < 2 ** 31 - 128)
 
 
 def _gemm_eligible(corpus: torch.Tensor, queries: torch.Tensor, k: int) -> bool:
-    return (corpus.dtype in (torch.bfloat16, torch.float16) and queries.dtype == corpus.dtype and k <= 16
-            and corpus.shape[1] % 8 == 0 and corpus.data_ptr() % 16 == 0 and queries.data_ptr() % 16 == 0
-            and corpus.shape[0] < 2 ** 31)
+    return _lowp_eligible(corpus, queries) and k <= 16
+
+
+def _tcstream_eligible(corpus: torch.Tensor, queries: torch.Tensor, k: int) -> bool:
+    return _lowp_eligible(corpus, queries) and k <= 1024
+
+
+def choose_algo(corpus: torch.Tensor, queries: torch.Tensor, k: int) -> str:
+    b = queries.shape[0]
+    if b >= GEMM_MIN_BATCH and _gemm_eligible(corpus, queries, k):
+        return "gemm"
+    if b >= TC_MIN_BATCH and _tcstream_eligible(corpus, queries, k):
+        return "tcstream"
+    return "stream"
 
 
 def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_base: int = 0,
@@ -77,31 +100,40 @@ def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_ba
     k = int(k)
     if k <= 0 or n <= 0 or b <= 0:
         raise ValueError("k, corpus rows and query rows must be positive")
-    if algo not in ("auto", "stream", "gemm"):
-        raise ValueError("algo must be 'auto', 'stream' or 'gemm'")
-    use_gemm = algo == "gemm" or (algo == "auto" and b >= GEMM_MIN_BATCH and _gemm_eligible(corpus, queries, k))
-    if use_gemm and not _gemm_eligible(corpus, queries, k):
-        raise ValueError("the tensor-core path needs bf16/fp16 corpus and queries of one dtype, k <= 16, dim % 8 == 0")
+    if algo not in _ALGOS:
+        raise ValueError(f"algo must be one of {_ALGOS}")
+    if algo == "auto":
+        algo = choose_algo(corpus, queries, k)
+    if algo == "gemm" and not _gemm_eligible(corpus, queries, k):
+        raise ValueError("the tensor-core GEMM path needs bf16/fp16 corpus and queries of one dtype, k <= 16, dim % 8 == 0")
+    if algo == "tcstream" and not _tcstream_eligible(corpus, queries, k):
+        raise ValueError("the tensor-core streaming path needs bf16/fp16 corpus and queries of one dtype, k <= 1024, dim % 8 == 0")
     lib = _lib.load()
     with torch.cuda.device(dev):
         scores = torch.empty((b, k), dtype=torch.float32, device=dev)
         idx = torch.empty((b, k), dtype=torch.int64, device=dev)
         keys = torch.empty((b, k), dtype=torch.int64, device=dev) if return_keys else None
-        if use_gemm:
+        keys_ptr = keys.data_ptr() if keys is not None else None
+        if algo == "gemm":
             need = lib.ss_cosine_topk_gemm_workspace_bytes(n, d, b, k)
             ws = workspace(dev, need, "gemm")
             st = lib.ss_cosine_topk_gemm(
                 corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, k, int(index_base), ws.data_ptr(),
-                ws.numel(), keys.data_ptr() if keys is not None else None, scores.data_ptr(), idx.data_ptr(),
-                _stream_ptr(dev))
+                ws.numel(), keys_ptr, scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
             _lib.check(st, "ss_cosine_topk_gemm")
+        elif algo == "tcstream":
+            need = lib.ss_cosine_topk_tcstream_workspace_bytes(n, d, b, k)
+            ws = workspace(dev, need)
+            st = lib.ss_cosine_topk_tcstream(
+                corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, k, int(index_base), ws.data_ptr(),
+                ws.numel(), keys_ptr, scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
+            _lib.check(st, "ss_cosine_topk_tcstream")
         else:
             need = lib.ss_cosine_topk_stream_workspace_bytes(n, d, _dtype_code(corpus), b, k)
             ws = workspace(dev, need)
             st = lib.ss_cosine_topk_stream(
                 corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, _dtype_code(queries), k,
-                int(index_base), ws.data_ptr(), ws.numel(), keys.data_ptr() if keys is not None else None,
-                scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
+                int(index_base), ws.data_ptr(), ws.numel(), keys_ptr, scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
             _lib.check(st, "ss_cosine_topk_stream")
     if return_keys:
         return scores, idx, keys
