@@ -10,11 +10,14 @@
 namespace ss {
 
 // One CTA per query.  Lists are staged in shared memory when they fit (they always do for the
-// shapes of BASELINE.json: 148 x 100 keys = 118 KB at most).
-__global__ void __launch_bounds__(256) topk_merge_kernel(const uint64_t* __restrict__ keys_in, int n_lists, int k_in,
-                                                         long long query_stride, long long list_stride, int k_out,
-                                                         uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
-                                                         long long* __restrict__ out_indices, int stage_in_smem) {
+// shapes of BASELINE.json: 148 x 100 keys = 118 KB at most), followed by the survivor scratch of
+// the fast path.
+constexpr int kMergeThreads = 512;
+
+__global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(const uint64_t* __restrict__ keys_in, int n_lists, int k_in,
+                                                                   long long query_stride, long long list_stride, int k_out,
+                                                                   uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
+                                                                   long long* __restrict__ out_indices, int stage_in_smem) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
   __shared__ uint64_t scratch[2];
   const int q = blockIdx.x;
@@ -23,16 +26,35 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const uint64_t* __restr
   out.keys = out_keys ? out_keys + static_cast<size_t>(q) * k_out : nullptr;
   out.scores = out_scores ? out_scores + static_cast<size_t>(q) * k_out : nullptr;
   out.indices = out_indices ? out_indices + static_cast<size_t>(q) * k_out : nullptr;
+  uint64_t* surv = reinterpret_cast<uint64_t*>(merge_smem);
   if (stage_in_smem) {
-    uint64_t* sl = reinterpret_cast<uint64_t*>(merge_smem);
-    for (int c = threadIdx.x; c < n_lists * k_in; c += blockDim.x) {
-      const int pl = c / k_in, i = c - pl * k_in;
-      sl[c] = base[static_cast<size_t>(pl) * list_stride + i];
+    uint64_t* sl = surv + kMergeSurvivorCap;
+    const int total = n_lists * k_in;
+    if (list_stride == k_in && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+      // contiguous [list][k] block: flat 16-byte copy, four loads in flight per thread
+      const int nvec = total >> 1;
+      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(base);
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(sl);
+      int c = threadIdx.x;
+      for (; c + 3 * kMergeThreads < nvec; c += 4 * kMergeThreads) {
+        const ulonglong2 v0 = src[c], v1 = src[c + kMergeThreads], v2 = src[c + 2 * kMergeThreads], v3 = src[c + 3 * kMergeThreads];
+        dst[c] = v0;
+        dst[c + kMergeThreads] = v1;
+        dst[c + 2 * kMergeThreads] = v2;
+        dst[c + 3 * kMergeThreads] = v3;
+      }
+      for (; c < nvec; c += kMergeThreads) dst[c] = src[c];
+      if ((total & 1) && threadIdx.x == 0) sl[total - 1] = base[total - 1];
+    } else {
+      for (int c = threadIdx.x; c < total; c += blockDim.x) {
+        const int pl = c / k_in, i = c - pl * k_in;
+        sl[c] = base[static_cast<size_t>(pl) * list_stride + i];
+      }
     }
     __syncthreads();
-    block_merge_lists(sl, n_lists, k_in, k_in, k_out, out, scratch);
+    block_merge_lists(sl, n_lists, k_in, k_in, k_out, out, scratch, surv);
   } else {
-    block_merge_lists(base, n_lists, k_in, list_stride, k_out, out, scratch);
+    block_merge_lists(base, n_lists, k_in, list_stride, k_out, out, scratch, surv);
   }
 }
 
@@ -65,11 +87,12 @@ extern "C" int ss_topk_merge(const uint64_t* keys_in, int n_lists, int n_queries
   if (n_lists <= 0 || n_queries <= 0 || k_in <= 0 || k_out <= 0)
     return fail(SS_ERR_INVALID_ARG, "ss_topk_merge: sizes must be positive");
   const size_t bytes = static_cast<size_t>(n_lists) * k_in * 8;
-  const int stage = bytes + 1024 <= smem_optin() ? 1 : 0;
-  const size_t dyn = stage ? bytes : 0;
+  const size_t surv_bytes = static_cast<size_t>(kMergeSurvivorCap) * 8;
+  const int stage = bytes + surv_bytes + 1024 <= smem_optin() ? 1 : 0;
+  const size_t dyn = surv_bytes + (stage ? bytes : 0);
   if (dyn > 48 * 1024)
     SS_CUDA_CHECK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
-  topk_merge_kernel<<<n_queries, 256, dyn, static_cast<cudaStream_t>(stream)>>>(
+  topk_merge_kernel<<<n_queries, kMergeThreads, dyn, static_cast<cudaStream_t>(stream)>>>(
       keys_in, n_lists, k_in, query_stride, list_stride, k_out, out_keys, out_scores,
       reinterpret_cast<long long*>(out_indices), stage);
   SS_CUDA_CHECK(cudaGetLastError());

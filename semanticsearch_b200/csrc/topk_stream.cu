@@ -156,7 +156,8 @@ __device__ __forceinline__ void cta_epilogue(const StreamParams& p, const uint64
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();  // acquire: every other CTA's list is visible now
   const int P = gridDim.x;
-  const bool stage = stage_area != nullptr && static_cast<size_t>(P) * p.k * 8 <= stage_bytes;
+  const bool stage = stage_area != nullptr && (static_cast<size_t>(P) * p.k + kMergeSurvivorCap) * 8 <= stage_bytes;
+  uint64_t* surv = stage ? stage_area + static_cast<size_t>(P) * p.k : nullptr;
   for (int b = 0; b < nq; ++b) {
     const uint64_t* src = p.partial + static_cast<size_t>(q0 + b) * P * p.k;
     if (stage) {
@@ -169,7 +170,7 @@ __device__ __forceinline__ void cta_epilogue(const StreamParams& p, const uint64
     out.keys = p.out_keys ? p.out_keys + o : nullptr;
     out.scores = p.out_scores ? p.out_scores + o : nullptr;
     out.indices = p.out_indices ? p.out_indices + o : nullptr;
-    block_merge_lists(src, P, p.k, p.k, p.k, out, scratch);
+    block_merge_lists(src, P, p.k, p.k, p.k, out, scratch, surv);
     __syncthreads();
   }
 }
