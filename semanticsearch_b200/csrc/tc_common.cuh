@@ -19,6 +19,61 @@ __device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// ---- thread-block clusters / CTA pairs -------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (.release.cta): a cluster-scope release would cost a GPU-wide memory barrier per arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// CTA-pair TMA load: data lands in this CTA's shared memory, the transaction bytes are credited
+// to the mbarrier at `bar_cluster_addr` (the pair leader's barrier).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// Pair MMA (issued by the leader CTA only): M = 256 split over the two CTAs' TMEM, each CTA
+// supplies its own A rows and its half of B from the same shared-memory offsets.
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the mbarrier at the same shared-memory offset in both CTAs of the pair once every
+// previously issued pair MMA has completed.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -94,6 +149,49 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc(int ab_format, int m, int n) {
   return (1u << 4) | (static_cast<uint32_t>(ab_format) << 7) | (static_cast<uint32_t>(ab_format) << 10) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ---- lean single-lane issue ------------------------------------------------------------------------
+// The MMA warp runs its loop on all 32 lanes with warp-uniform state and elects one lane per
+// instruction (the CUTLASS idiom): the compiler then keeps descriptors in uniform registers and
+// the issue loop stays far below the execution time of the MMAs it feeds.  The 64-bit shared-
+// memory descriptor is passed as (lo, hi): stepping along K only ever touches the low word.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+constexpr uint32_t kSmemDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+template <int CG>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) {
+    if (CG == 1) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "setp.ne.b32 p, %5, 0;\n\t"
+          "mov.b64 da, {%1, %3};\n\t"
+          "mov.b64 db, {%2, %3};\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+          ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(kSmemDescHi), "r"(idesc), "r"(accumulate)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "setp.ne.b32 p, %5, 0;\n\t"
+          "mov.b64 da, {%1, %3};\n\t"
+          "mov.b64 db, {%2, %3};\n\t"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+          ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(kSmemDescHi), "r"(idesc), "r"(accumulate)
+          : "memory");
+    }
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  if (elect_one()) {
+    if (CG == 1) umma_commit(bar); else umma_commit_pair(bar);
+  }
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------------

@@ -25,12 +25,22 @@ namespace ss {
 constexpr int G_BM = 128;
 constexpr int G_BN = 256;
 constexpr int G_BK = 64;
-constexpr int G_STAGES = 4;
+constexpr int G_MAX_STAGES = 6;
 constexpr int G_A_BYTES = G_BM * G_BK * 2;
-constexpr int G_B_BYTES = G_BN * G_BK * 2;
-constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
-constexpr int G_THREADS = 192;
-constexpr int G_EPI_THREADS = 128;
+// CG = 1: one CTA per 128 x 256 tile.  CG = 2: a CTA pair (two SMs of one TPC) computes a 256 x 256
+// tile with tcgen05.mma.cta_group::2 — each CTA stages its own 128 query rows and only HALF of the
+// corpus tile, so the L2 -> shared-memory traffic and the shared-memory bandwidth per MMA drop by a
+// third and the ring gets deeper.
+template <int CG> struct GemmCfg {
+  static constexpr int kBRows = G_BN / CG;                 // corpus rows this CTA stages per tile
+  static constexpr int kBBytes = kBRows * G_BK * 2;
+  static constexpr int kStageBytes = G_A_BYTES + kBBytes;  // 48 KB / 32 KB
+  static constexpr int kMaxStages = CG == 1 ? 4 : G_MAX_STAGES;
+};
+constexpr int G_EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int G_THREADS = (2 + G_EPI_WARPS) * 32;
+constexpr int G_EPI_THREADS = G_EPI_WARPS * 32;
+constexpr int G_EPI_COLS = G_BN / (G_EPI_WARPS / 4);  // columns per epilogue thread and tile
 constexpr int G_TMEM_COLS = 512;
 
 struct GemmParams {
@@ -39,17 +49,16 @@ struct GemmParams {
   int dim;
   int k;
   uint32_t index_base;
-  int n_qb;
+  int n_qb;  // query blocks of 128 * CG rows
   long long n_tiles;
   int tiles_per_chunk;
   int n_chunks;
   long long n_units;
-  const float* inv_c;
+  int stages;
+  const float* inv_c;  // padded to a multiple of G_BN entries, NaN past n_rows (never selected)
   const float* inv_q;
-  uint64_t* partial;  // [n_chunks][n_queries][k]
+  uint64_t* partial;  // [n_chunks * 2][n_queries][k]: one list per (chunk, column half)
 };
-
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Per-thread top-k list in shared memory, entry j of epilogue thread e at list[j * 128 + e]
 // (conflict-free across a warp).  Sorted descending; strict '>' keeps the earlier (lower-index)
@@ -73,20 +82,28 @@ __device__ __noinline__ float epi_list_insert(ScoreIdx* list, int k, float sc, i
   return list[(k - 1) * G_EPI_THREADS].v;
 }
 
+template <int CG>
 __global__ void __launch_bounds__(G_THREADS, 1)
 cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                         const GemmParams p, const uint32_t idesc) {
+  constexpr int G_STAGE_BYTES = GemmCfg<CG>::kStageBytes;
+  const int G_STAGES = p.stages;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;  // rank 0 of a pair issues the MMAs
+  const int n_workers = static_cast<int>(gridDim.x) / CG;       // CTAs (CG = 1) or CTA pairs (CG = 2)
+  const int worker = static_cast<int>(blockIdx.x) / CG;
   extern __shared__ unsigned char gemm_smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
   unsigned char* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + G_STAGES * G_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + G_STAGES;
-  uint64_t* tmem_full = empty_bar + G_STAGES;
+  float* sinv = reinterpret_cast<float*>(tiles + static_cast<size_t>(G_STAGES) * G_STAGE_BYTES);  // [2][G_BN] corpus inverse norms
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sinv + 2 * G_BN);
+  uint64_t* empty_bar = full_bar + G_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + G_MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* sinv = reinterpret_cast<float*>(tmem_ptr_s + 4);  // [2][G_BN] corpus inverse norms of the tile in flight
-  ScoreIdx* lists = reinterpret_cast<ScoreIdx*>(sinv + 2 * G_BN);  // [k][128] per-thread top-k lists
+  uint64_t* inv_full = tmem_empty + 2;
+  uint64_t* inv_empty = inv_full + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(inv_empty + 2);
+  ScoreIdx* lists = reinterpret_cast<ScoreIdx*>(tmem_ptr_s + 4);  // [k][G_EPI_THREADS] per-thread top-k lists
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.dim + G_BK - 1) / G_BK;
@@ -100,32 +117,54 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], G_EPI_WARPS * CG);  // the epilogue warps of every CTA that shares the accumulator
+      mbar_init(&inv_full[a], 1);
+      mbar_init(&inv_empty[a], G_EPI_WARPS);
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_s, G_TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_pair(tmem_ptr_s, G_TMEM_COLS); else tmem_alloc(tmem_ptr_s, G_TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int chunk = static_cast<int>(u / p.n_qb), qb = static_cast<int>(u % p.n_qb);
+      int s = 0, ia = 0;
+      uint32_t ph = 0, ia_ph = 0;
+      for (long long u = worker; u < p.n_units; u += n_workers) {
+        const int chunk = static_cast<int>(u / p.n_qb), qb = static_cast<int>(u % p.n_qb) * CG + static_cast<int>(cta_rank);
         const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
         const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
         for (long long t = t0; t < t1; ++t) {
+          // this tile's 256 corpus inverse norms (1 KB) ride the TMA engine too
+          mbar_wait(&inv_empty[ia], ia_ph ^ 1u);
+          mbar_arrive_expect_tx(&inv_full[ia], G_BN * 4);
+          bulk_copy_g2s(sinv + ia * G_BN, p.inv_c + t * G_BN, G_BN * 4, &inv_full[ia]);
+          if (++ia == 2) {
+            ia = 0;
+            ia_ph ^= 1u;
+          }
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty_bar[s], ph ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[s], G_STAGE_BYTES);
-            unsigned char* a_dst = tiles + s * G_STAGE_BYTES;
-            tma_load_2d(a_dst, &tmap_q, &full_bar[s], kb * G_BK, qb * G_BM);
-            tma_load_2d(a_dst + G_A_BYTES, &tmap_c, &full_bar[s], kb * G_BK, static_cast<int>(t * G_BN));
+            unsigned char* a_dst = tiles + static_cast<size_t>(s) * G_STAGE_BYTES;
+            if (CG == 1) {
+              mbar_arrive_expect_tx(&full_bar[s], G_STAGE_BYTES);
+              tma_load_2d(a_dst, &tmap_q, &full_bar[s], kb * G_BK, qb * G_BM);
+              tma_load_2d(a_dst + G_A_BYTES, &tmap_c, &full_bar[s], kb * G_BK, static_cast<int>(t * G_BN));
+            } else {
+              // both CTAs credit the LEADER's barrier, which expects the bytes of the whole pair
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * G_STAGE_BYTES);
+              const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+              tma_load_2d_pair(a_dst, &tmap_q, lead_bar, kb * G_BK, qb * G_BM);
+              tma_load_2d_pair(a_dst + G_A_BYTES, &tmap_c, lead_bar, kb * G_BK,
+                               static_cast<int>(t * G_BN) + static_cast<int>(cta_rank) * GemmCfg<CG>::kBRows);
+            }
             if (++s == G_STAGES) {
               s = 0;
               ph ^= 1u;
@@ -135,10 +174,11 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (pair leader only when CG = 2) =====================
     int s = 0, acc = 0;
     uint32_t ph = 0, acc_ph = 0;
-    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    const uint32_t tiles_lo = smem_desc_lo(smem_u32(tiles));
+    for (long long u = worker; cta_rank == 0 && u < p.n_units; u += n_workers) {
       const int chunk = static_cast<int>(u / p.n_qb);
       const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
       const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
@@ -149,17 +189,13 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);  // TMA bytes have landed
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(tiles + s * G_STAGE_BYTES);
-            const uint64_t da = make_smem_desc(a_addr);
-            const uint64_t db = make_smem_desc(a_addr + G_A_BYTES);
+          const uint32_t a_lo = tiles_lo + static_cast<uint32_t>(s) * (G_STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (G_A_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < G_BK / 16; ++k)  // +32 bytes (2 x 16-byte units) per K=16 step inside the swizzle atom
-              umma_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[s]);                      // frees the smem stage when these MMAs retire
-            if (kb == nkb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-          }
-          __syncwarp();
+          for (int k = 0; k < G_BK / 16; ++k)  // +32 bytes (2 x 16-byte units) per K=16 step inside the swizzle atom
+            umma_f16_lohi<CG>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_elect<CG>(&empty_bar[s]);                      // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if (kb == nkb - 1) umma_commit_elect<CG>(&tmem_full[acc]);  // accumulator complete -> epilogue
           if (++s == G_STAGES) {
             s = 0;
             ph ^= 1u;
@@ -172,15 +208,18 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
     }
   } else {
-    // ===================== epilogue: one query row per thread =====================
+    // ===================== epilogue: one query row x half of the tile's columns per thread =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;          // which 128 columns of the 256-column tile
     const int row = quad * 32 + lane;          // query row inside the 128-row block
-    const int et = (warp - 2) * 32 + lane;     // 0..127 among epilogue threads
+    const int et = (warp - 2) * 32 + lane;     // 0..255 among epilogue threads
     ScoreIdx* my_list = lists + et;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int chunk = static_cast<int>(u / p.n_qb), qb = static_cast<int>(u % p.n_qb);
+    const uint32_t lead_tmem_empty0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+    const uint32_t lead_tmem_empty1 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u;
+    for (long long u = worker; u < p.n_units; u += n_workers) {
+      const int chunk = static_cast<int>(u / p.n_qb), qb = static_cast<int>(u % p.n_qb) * CG + static_cast<int>(cta_rank);
       const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
       const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
       const int query = qb * G_BM + row;
@@ -192,34 +231,17 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         my_list[j * G_EPI_THREADS] = e;
       }
       float thr = -INFINITY;
-      // corpus inverse norms of the first tile (NaN for rows past the end: never selected);
-      // later tiles are prefetched one tile ahead so the global-load latency stays hidden
-      float inv_next[G_BN / G_EPI_THREADS];
-#pragma unroll
-      for (int h = 0; h < G_BN / G_EPI_THREADS; ++h) {
-        const long long gr = t0 * G_BN + h * G_EPI_THREADS + et;
-        inv_next[h] = gr < p.n_rows ? __ldg(p.inv_c + gr) : __int_as_float(0x7fc00000);
-      }
       for (long long t = t0; t < t1; ++t) {
-        float* inv_tile = sinv + acc * G_BN;
-#pragma unroll
-        for (int h = 0; h < G_BN / G_EPI_THREADS; ++h) inv_tile[h * G_EPI_THREADS + et] = inv_next[h];
-        epi_bar_sync();
-        if (t + 1 < t1) {
-#pragma unroll
-          for (int h = 0; h < G_BN / G_EPI_THREADS; ++h) {
-            const long long gr = (t + 1) * G_BN + h * G_EPI_THREADS + et;
-            inv_next[h] = gr < p.n_rows ? __ldg(p.inv_c + gr) : __int_as_float(0x7fc00000);
-          }
-        }
+        const float* inv_tile = sinv + acc * G_BN + half * G_EPI_COLS;
+        mbar_wait(&inv_full[acc], acc_ph);
         mbar_wait(&tmem_full[acc], acc_ph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * G_BN);
-        const int col_base = static_cast<int>(t * G_BN);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * G_BN + half * G_EPI_COLS);
+        const int col_base = static_cast<int>(t * G_BN) + half * G_EPI_COLS;
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
 #pragma unroll 1
-        for (int c0 = 0; c0 < G_BN; c0 += 64) {
+        for (int c0 = 0; c0 < G_EPI_COLS; c0 += 64) {
           tmem_ld_wait();                                   // ra = columns c0 .. c0+31
           tmem_ld32(taddr + static_cast<uint32_t>(c0 + 32), rb);  // in flight while ra is processed
           {
@@ -243,7 +265,7 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
           }
           tmem_ld_wait();                                   // rb = columns c0+32 .. c0+63
-          if (c0 + 64 < G_BN) tmem_ld32(taddr + static_cast<uint32_t>(c0 + 64), ra);
+          if (c0 + 64 < G_EPI_COLS) tmem_ld32(taddr + static_cast<uint32_t>(c0 + 64), ra);
           {
             float m = -INFINITY;
             float x[32];
@@ -267,14 +289,17 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          mbar_arrive(&inv_empty[acc]);
+          if (CG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_cluster(acc ? lead_tmem_empty1 : lead_tmem_empty0);
+        }
         if (++acc == 2) {
           acc = 0;
           acc_ph ^= 1u;
         }
       }
       if (query < p.n_queries) {
-        uint64_t* out = p.partial + (static_cast<size_t>(chunk) * p.n_queries + query) * p.k;
+        uint64_t* out = p.partial + ((static_cast<size_t>(chunk) * 2 + half) * p.n_queries + query) * p.k;
         for (int j = 0; j < p.k; ++j) {
           const ScoreIdx e = my_list[j * G_EPI_THREADS];
           out[j] = e.ix >= 0 ? make_key(e.v, p.index_base + static_cast<uint32_t>(e.ix)) : 0ull;
@@ -284,17 +309,22 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, G_TMEM_COLS);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, G_TMEM_COLS); else tmem_dealloc(tmem_base, G_TMEM_COLS);
   }
 }
 
 // ---- vectorised row inverse norms (pre-pass over the corpus, HBM-bound) -------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) row_inv_norms_vec_kernel(const T* __restrict__ rows, long long n_rows, int dim,
-                                                                float zero_value, float* __restrict__ out) {
+                                                                float zero_value, float* __restrict__ out, long long n_fill) {
   constexpr int NP = Pairs<T>::NP;
+  // entries past the last row (up to the padded length) are NaN: such columns are never selected
+  for (long long i = n_rows + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_fill;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __int_as_float(0x7fc00000);
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -324,10 +354,11 @@ __global__ void __launch_bounds__(256) row_inv_norms_vec_kernel(const T* __restr
 }
 
 template <typename T>
-static cudaError_t launch_inv_norms_vec(const void* rows, long long n_rows, int dim, float zero_value, float* out, cudaStream_t st) {
+static cudaError_t launch_inv_norms_vec(const void* rows, long long n_rows, int dim, float zero_value, float* out, long long n_fill,
+                                        cudaStream_t st) {
   const long long want = (n_rows + 15) / 16;
   const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(sm_count()) * 16)));
-  row_inv_norms_vec_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(rows), n_rows, dim, zero_value, out);
+  row_inv_norms_vec_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(rows), n_rows, dim, zero_value, out, n_fill);
   return cudaGetLastError();
 }
 
@@ -338,11 +369,14 @@ struct GemmPlan {
   int n_chunks;
 };
 
+static int gemm_cta_group(int n_queries) { return (n_queries > G_BM && sm_count() % 2 == 0) ? 2 : 1; }
+
 static GemmPlan make_gemm_plan(long long n_rows, int n_queries) {
   GemmPlan g;
-  g.n_qb = (n_queries + G_BM - 1) / G_BM;
+  const int cg = gemm_cta_group(n_queries);
+  g.n_qb = (n_queries + G_BM * cg - 1) / (G_BM * cg);
   g.n_tiles = (n_rows + G_BN - 1) / G_BN;
-  const long long target_units = static_cast<long long>(sm_count()) * 8;
+  const long long target_units = static_cast<long long>(sm_count() / cg) * 8;
   long long n_chunks = std::max<long long>(1, (target_units + g.n_qb - 1) / g.n_qb);
   n_chunks = std::min<long long>(n_chunks, std::max<long long>(1, g.n_tiles / 8));  // at least ~8 tiles per chunk
   g.tiles_per_chunk = static_cast<int>((g.n_tiles + n_chunks - 1) / n_chunks);
@@ -358,8 +392,8 @@ extern "C" size_t ss_cosine_topk_gemm_workspace_bytes(int64_t n_rows, int dim, i
   (void)dim;
   if (n_rows <= 0 || n_queries <= 0 || k <= 0) return 0;
   const GemmPlan g = make_gemm_plan(n_rows, n_queries);
-  return align_up(static_cast<size_t>(n_rows) * 4, 256) + align_up(static_cast<size_t>(n_queries) * 4, 256) +
-         align_up(static_cast<size_t>(g.n_chunks) * n_queries * k * 8, 256) + 256;
+  return align_up(static_cast<size_t>(n_rows), G_BN) * 4 + align_up(static_cast<size_t>(n_queries) * 4, 256) +
+         align_up(static_cast<size_t>(g.n_chunks) * 2 * n_queries * k * 8, 256) + 256;
 }
 
 extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, int dtype, const void* queries, int n_queries,
@@ -379,23 +413,25 @@ extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, 
 
   unsigned char* ws = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(workspace), 256));
   float* inv_c = reinterpret_cast<float*>(ws);
-  ws += align_up(static_cast<size_t>(n_rows) * 4, 256);
+  const long long n_fill = static_cast<long long>(align_up(static_cast<size_t>(n_rows), G_BN));
+  ws += static_cast<size_t>(n_fill) * 4;
   float* inv_q = reinterpret_cast<float*>(ws);
   ws += align_up(static_cast<size_t>(n_queries) * 4, 256);
   uint64_t* partial = reinterpret_cast<uint64_t*>(ws);
 
   cudaError_t e;
   if (dtype == SS_BF16) {
-    e = launch_inv_norms_vec<__nv_bfloat16>(corpus, n_rows, dim, 1.0f, inv_c, st);
-    if (e == cudaSuccess) e = launch_inv_norms_vec<__nv_bfloat16>(queries, n_queries, dim, 1.0f, inv_q, st);
+    e = launch_inv_norms_vec<__nv_bfloat16>(corpus, n_rows, dim, 1.0f, inv_c, n_fill, st);
+    if (e == cudaSuccess) e = launch_inv_norms_vec<__nv_bfloat16>(queries, n_queries, dim, 1.0f, inv_q, 0, st);
   } else {
-    e = launch_inv_norms_vec<__half>(corpus, n_rows, dim, 1.0f, inv_c, st);
-    if (e == cudaSuccess) e = launch_inv_norms_vec<__half>(queries, n_queries, dim, 1.0f, inv_q, st);
+    e = launch_inv_norms_vec<__half>(corpus, n_rows, dim, 1.0f, inv_c, n_fill, st);
+    if (e == cudaSuccess) e = launch_inv_norms_vec<__half>(queries, n_queries, dim, 1.0f, inv_q, 0, st);
   }
   if (e != cudaSuccess) return cuda_fail(e, "row_inv_norms_vec launch");
 
+  const int cg = gemm_cta_group(n_queries);
   CUtensorMap tmap_q, tmap_c;
-  if (!make_tmap_rows(&tmap_q, queries, dtype, n_queries, dim, G_BM) || !make_tmap_rows(&tmap_c, corpus, dtype, n_rows, dim, G_BN))
+  if (!make_tmap_rows(&tmap_q, queries, dtype, n_queries, dim, G_BM) || !make_tmap_rows(&tmap_c, corpus, dtype, n_rows, dim, G_BN / cg))
     return fail(SS_ERR_CUDA, "ss_cosine_topk_gemm: cuTensorMapEncodeTiled failed");
 
   const GemmPlan g = make_gemm_plan(n_rows, n_queries);
@@ -413,17 +449,40 @@ extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, 
   p.inv_c = inv_c;
   p.inv_q = inv_q;
   p.partial = partial;
-  const uint32_t idesc = make_idesc(dtype == SS_BF16 ? 1 : 0, G_BM, G_BN);
-  const size_t smem = static_cast<size_t>(G_STAGES) * G_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4 +
-                      static_cast<size_t>(k) * G_EPI_THREADS * sizeof(ScoreIdx);
-  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(sm_count(), p.n_units)));
-  e = cudaFuncSetAttribute(cosine_topk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e == cudaSuccess) {
-    ProfileScope prof(st);
-    cosine_topk_gemm_kernel<<<grid, G_THREADS, smem, st>>>(tmap_q, tmap_c, p, idesc);
-    e = cudaGetLastError();
+  const uint32_t idesc = make_idesc(dtype == SS_BF16 ? 1 : 0, G_BM * cg, G_BN);
+  const size_t per_stage = cg == 2 ? GemmCfg<2>::kStageBytes : GemmCfg<1>::kStageBytes;
+  const size_t fixed = 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4 + static_cast<size_t>(k) * G_EPI_THREADS * sizeof(ScoreIdx);
+  p.stages = static_cast<int>(std::min<size_t>(cg == 2 ? GemmCfg<2>::kMaxStages : GemmCfg<1>::kMaxStages, (smem_optin() - fixed) / per_stage));
+  if (p.stages < 2) return fail(SS_ERR_UNSUPPORTED, "ss_cosine_topk_gemm: not enough shared memory");
+  const size_t smem = fixed + static_cast<size_t>(p.stages) * per_stage;
+  const int workers = static_cast<int>(std::max<long long>(1, std::min<long long>(sm_count() / cg, p.n_units)));
+  if (cg == 1) {
+    e = cudaFuncSetAttribute(cosine_topk_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) {
+      ProfileScope prof(st);
+      cosine_topk_gemm_kernel<1><<<workers, G_THREADS, smem, st>>>(tmap_q, tmap_c, p, idesc);
+      e = cudaGetLastError();
+    }
+  } else {
+    e = cudaFuncSetAttribute(cosine_topk_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) {
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(static_cast<unsigned int>(workers * 2));
+      lc.blockDim = dim3(G_THREADS);
+      lc.dynamicSmemBytes = smem;
+      lc.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;  // CTA pair: two SMs of one TPC
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      lc.attrs = attr;
+      lc.numAttrs = 1;
+      ProfileScope prof(st);
+      e = cudaLaunchKernelEx(&lc, cosine_topk_gemm_kernel<2>, tmap_q, tmap_c, p, idesc);
+    }
   }
   if (e != cudaSuccess) return cuda_fail(e, "cosine_topk_gemm launch");
-  return ss_topk_merge(partial, g.n_chunks, n_queries, k, k, static_cast<int64_t>(n_queries) * k, k, out_keys, out_scores,
+  return ss_topk_merge(partial, g.n_chunks * 2, n_queries, k, k, static_cast<int64_t>(n_queries) * k, k, out_keys, out_scores,
                        out_indices, stream);
 }
