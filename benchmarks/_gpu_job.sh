@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_gemm.py -x -q 2>&1 | tail -5
-timeout 300 python benchmarks/sweep_topk.py --batches 128,1024,4096 --algos gemm --steps 5 2>&1 | tee gpurun_out/sweep_gemm.jsonl
+timeout 600 python -m pytest tests/test_gpu_simmatrix_tc.py -x -q -s 2>&1 | tail -25
+timeout 600 python benchmarks/bench_configs.py --config 2 --steps 5 2>&1 | tail -3

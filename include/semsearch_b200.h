@@ -134,6 +134,17 @@ int ss_segmented_plan_host(const int32_t* offsets_host, int n_docs, int64_t* s_o
 int ss_segmented_simmatrix(const float* rows, int dim, const int32_t* offsets, const int64_t* s_offsets,
                            const int32_t* tile_prefix, int n_docs, int64_t total_tiles, float* out_S, void* stream);
 
+/* K3 on the tensor cores (same outputs, same reference lines as ss_segmented_simmatrix): 128 x 128
+ * upper-triangular tiles, every fp32 operand split on the fly into tf32 hi + lo and multiplied as
+ * hi.hi + hi.lo + lo.hi with tcgen05.mma kind::tf32 (fp32 accumulation in TMEM), so |S - S_fp32| stays
+ * ~1e-6, inside the 1e-5 parity bound that plain TF32 would miss by two orders of magnitude.  Needs
+ * dim % 4 == 0 and 16-byte aligned rows.  ss_segmented_plan128_host (HOST pointers) lists the work units
+ * {doc, tile row, tile column, 0} (int32 x 4 each); call it with units_host = NULL to size the table. */
+int ss_segmented_plan128_host(const int32_t* offsets_host, int n_docs, int32_t* units_host, int64_t capacity_units,
+                              int64_t* total_units);
+int ss_segmented_simmatrix_tc(const float* rows, int64_t total_rows, int dim, const int32_t* offsets,
+                              const int64_t* s_offsets, const int32_t* units, int64_t n_units, float* out_S, void* stream);
+
 /* ---- K4: semantic-grouping threshold pass ------------------------------------------------------
  * Per document, from S (layout of K3): sim_sharp = sigmoid(((S-mu)/sigma)/tau) in fp32 with zero
  * diagonal (Method/Semantic_Grouping_Optimized.py:100-113), centrality (:115), the quantile

@@ -1,0 +1,379 @@
+// K3 (tensor-core form) — segmented sentence x sentence similarity matrices S_d = En_d . En_d^T on
+// the 5th-gen tensor cores with fp32-class accuracy (3xTF32 error-compensated products).
+//
+// Replaces the arithmetic of create_similarity_matrix (Method/semantic_common.py:158-164,186-191:
+// row L2 normalisation, then torch.mm / numpy matmul in fp32), the C99 similarity at
+// Method/Semantic_Splitter_Optimized.py:169 and the controller's diagnostic recomputations
+// (data_process/simple_chunk_controller.py:614,682,743) for a whole ragged batch in one launch.
+//
+// Parity needs |S - S_ref| <= 1e-5, which rules out plain TF32/BF16 products (1e-3).  Every fp32
+// operand x is split on the fly into hi = tf32(x) (round-to-nearest) and lo = x - hi (exact), and
+// each K step issues three kind::tf32 MMAs: hi.hi + hi.lo + lo.hi; the dropped lo.lo term and the
+// truncation of lo are ~2^-21 relative per product.  fp32 accumulation happens in TMEM.
+//
+// Work unit = one 128 x 128 upper-triangular tile (ti <= tj) of one document, listed in a host-built
+// unit table.  Persistent CTAs, 14 warps:
+//   warp 0      TMA producer : raw fp32 row tiles (128 rows x 32 floats, SWIZZLE_128B) of the tile's
+//                              row block (A) and column block (B) into a 3-stage ring
+//   warps 6-13  splitters    : one tile row per thread: rewrite the raw plane in place as `hi`, write
+//                              `lo` to a second plane (same swizzled offsets), accumulate the row's
+//                              sum of squares, fence.proxy.async and hand the stage to the MMA warp
+//   warp 1      MMA issuer   : 12 tcgen05.mma (M=128, N=16..128, K=8) per K block into a double-
+//                              buffered TMEM accumulator
+//   warps 2-5   epilogue     : tcgen05.ld, scale by 1/|e_i| 1/|e_j| (zero rows stay zero), write the
+//                              tile and, for off-diagonal tiles, its transpose; both writes are
+//                              coalesced (the transpose directly from the TMEM lane layout, the
+//                              direct tile through a padded shared-memory transpose).
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace ss {
+
+constexpr int S_BM = 128;
+constexpr int S_BK = 32;                    // fp32 elements per K block = one 128-byte swizzle atom
+constexpr int S_PLANE = S_BM * 128;         // 16 KB: 128 rows x 128 bytes
+constexpr int S_STAGE_BYTES = 4 * S_PLANE;  // A hi | B hi | A lo | B lo
+constexpr int S_STAGES = 3;
+constexpr int S_THREADS = 14 * 32;
+constexpr int S_TMEM_COLS = 512;  // 2 buffers x (main accumulator | correction accumulator) x 128 columns
+
+struct SimTcParams {
+  const int* offsets;          // [n_docs + 1] row offsets
+  const long long* s_offsets;  // [n_docs + 1] element offsets into out
+  const int4* units;           // [n_units] {doc, ti, tj, 0}
+  long long n_units;
+  int dim;
+  int nkb;
+  float* out;
+};
+
+struct SimUnit {
+  int row_base, n, ti, tj;
+  long long s_off;
+};
+
+__device__ __forceinline__ SimUnit load_unit(const SimTcParams& p, long long u) {
+  const int4 e = __ldg(p.units + u);
+  SimUnit r;
+  r.row_base = __ldg(p.offsets + e.x);
+  r.n = __ldg(p.offsets + e.x + 1) - r.row_base;
+  r.s_off = __ldg(p.s_offsets + e.x);
+  r.ti = e.y;
+  r.tj = e.z;
+  return r;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(kSmemDescHi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const SimTcParams p) {
+  extern __shared__ unsigned char simtc_smem_raw[];
+  unsigned char* smem = simtc_smem_raw + ((1024u - (smem_u32(simtc_smem_raw) & 1023u)) & 1023u);
+  unsigned char* tiles = smem;                                                       // [S_STAGES][64 KB]
+  float* scratch = reinterpret_cast<float*>(tiles + S_STAGES * S_STAGE_BYTES);      // [4 warps][32][33] transpose staging
+  float* inv_s = scratch + 4 * 32 * 33;                                              // [2][256]: 1/|row| of the A rows, then the B rows
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(inv_s + 2 * 256);
+  uint64_t* ready_bar = full_bar + S_STAGES;
+  uint64_t* empty_bar = ready_bar + S_STAGES;
+  uint64_t* tmem_full = empty_bar + S_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* norm_full = tmem_empty + 2;
+  uint64_t* norm_empty = norm_full + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(norm_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tmap_prefetch(&tmap_rows);
+    for (int s = 0; s < S_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ready_bar[s], 8);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&norm_full[a], 8);
+      mbar_init(&norm_empty[a], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_s, S_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const SimUnit un = load_unit(p, u);
+        const bool diag = un.ti == un.tj;
+        const int ra = un.row_base + un.ti * S_BM, rb = un.row_base + un.tj * S_BM;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          unsigned char* st = tiles + s * S_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], diag ? S_PLANE : 2 * S_PLANE);
+          tma_load_2d(st, &tmap_rows, &full_bar[s], kb * S_BK, ra);
+          if (!diag) tma_load_2d(st + S_PLANE, &tmap_rows, &full_bar[s], kb * S_BK, rb);
+          if (++s == S_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (all lanes run the loop, one elected lane issues) =====================
+    int s = 0, acc = 0;
+    uint32_t ph = 0, acc_ph = 0;
+    const uint32_t tiles_lo = smem_desc_lo(smem_u32(tiles));
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const SimUnit un = load_unit(p, u);
+      const bool diag = un.ti == un.tj;
+      const int ncols = min(S_BM, un.n - un.tj * S_BM);
+      const uint32_t idesc = make_idesc(2 /*tf32*/, S_BM, (ncols + 15) & ~15);
+      mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+      tc_fence_after();
+      // The tensor core truncates when it adds into the fp32 accumulator, a bias that grows with the
+      // number of accumulations at full magnitude.  The hi.hi products (96 MMAs at d = 768) therefore get
+      // an accumulator of their own; the 2 x 96 small cross terms go to a second one (their truncation
+      // error is ~1e-3 smaller) and the epilogue adds the two in fp32.
+      const uint32_t d_main = tmem_base + static_cast<uint32_t>(acc * 2 * S_BM);
+      const uint32_t d_corr = d_main + S_BM;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(&ready_bar[s], ph);  // hi / lo planes written and fenced by the splitters
+        tc_fence_after();
+        const uint32_t a_hi = tiles_lo + static_cast<uint32_t>(s) * (S_STAGE_BYTES >> 4);
+        const uint32_t b_hi = diag ? a_hi : a_hi + (S_PLANE >> 4);
+        const uint32_t a_lo = a_hi + (2 * S_PLANE >> 4);
+        const uint32_t b_lo = diag ? a_lo : a_hi + (3 * S_PLANE >> 4);
+#pragma unroll
+        for (int k = 0; k < S_BK / 8; ++k) {  // K = 8 tf32 per MMA = 32 bytes = 2 descriptor units
+          umma_tf32_lohi(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_tf32_lohi(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_tf32_lohi(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+        }
+        umma_commit_elect<1>(&empty_bar[s]);
+        if (kb == p.nkb - 1) umma_commit_elect<1>(&tmem_full[acc]);
+        if (++s == S_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_ph ^= 1u;
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== splitters: one tile row per thread =====================
+    const int srow = (warp - 6) * 32 + lane;  // 0..127: A rows, 128..255: B rows
+    const int r = srow & 127;
+    const uint32_t plane_off = srow < 128 ? 0u : static_cast<uint32_t>(S_PLANE);
+    int s = 0, acc = 0;
+    uint32_t ph = 0, acc_ph = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int4 e = __ldg(p.units + u);
+      const bool active = srow < 128 || e.y != e.z;  // diagonal tiles have no separate B rows
+      float ssq0 = 0.f, ssq1 = 0.f;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        if (active) {
+          unsigned char* base = tiles + s * S_STAGE_BYTES + plane_off + static_cast<uint32_t>(r) * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = (j ^ (r & 7)) * 16;  // conflict-free: 8 consecutive rows touch 8 distinct 16-byte chunks
+            const float4 v = *reinterpret_cast<const float4*>(base + c);
+            float4 hi, lo;
+            hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+            lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+            ssq0 = fmaf(v.x, v.x, fmaf(v.y, v.y, ssq0));
+            ssq1 = fmaf(v.z, v.z, fmaf(v.w, v.w, ssq1));
+            *reinterpret_cast<float4*>(base + c) = hi;
+            *reinterpret_cast<float4*>(base + 2 * S_PLANE + c) = lo;
+          }
+          fence_proxy_async();  // generic-proxy writes above -> visible to the tensor core's async-proxy reads
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready_bar[s]);
+        if (++s == S_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      const float ssq = ssq0 + ssq1;
+      mbar_wait(&norm_empty[acc], acc_ph ^ 1u);
+      // zero rows stay zero (reference: norm 0 -> 1e-9, and 0 / 1e-9 == 0)
+      if (active) inv_s[acc * 256 + srow] = ssq > 0.f ? 1.0f / sqrtf(ssq) : 0.f;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&norm_full[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_ph ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue: one tile row (TMEM lane) per thread =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    float* scr = scratch + (warp - 2) * 32 * 33;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const SimUnit un = load_unit(p, u);
+      const bool diag = un.ti == un.tj;
+      const int n = un.n;
+      float* S = p.out + un.s_off;
+      const int gr = un.ti * S_BM + row;          // this thread's global row inside the document
+      const int gc0 = un.tj * S_BM;
+      const int ncols = min(S_BM, n - gc0);
+      mbar_wait(&norm_full[acc], acc_ph);
+      const float* inv_a = inv_s + acc * 256;
+      const float* inv_b = diag ? inv_a : inv_a + 128;
+      const float my_inv = inv_a[row];
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 2 * S_BM);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        float x[32];
+        {
+          uint32_t raw[32], cor[32];
+          tmem_ld32(taddr + static_cast<uint32_t>(c0), raw);
+          tmem_ld32(taddr + static_cast<uint32_t>(S_BM + c0), cor);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 ib = *reinterpret_cast<const float4*>(inv_b + c0 + j);
+            x[j] = (__uint_as_float(raw[j]) + __uint_as_float(cor[j])) * (my_inv * ib.x);
+            x[j + 1] = (__uint_as_float(raw[j + 1]) + __uint_as_float(cor[j + 1])) * (my_inv * ib.y);
+            x[j + 2] = (__uint_as_float(raw[j + 2]) + __uint_as_float(cor[j + 2])) * (my_inv * ib.z);
+            x[j + 3] = (__uint_as_float(raw[j + 3]) + __uint_as_float(cor[j + 3])) * (my_inv * ib.w);
+          }
+        }
+        // transposed tile S[col][row]: lanes hold consecutive rows -> consecutive addresses.  Diagonal
+        // tiles mirror their strict upper triangle so that S is bit-for-bit symmetric.
+        if (gr < n) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gc = gc0 + c0 + j;
+            if (gc < n && (!diag || gc > gr)) S[static_cast<size_t>(gc) * n + gr] = x[j];
+          }
+        }
+        // direct tile S[row][col]: transpose 32 x 32 through padded shared memory so that lanes
+        // hold consecutive columns
+#pragma unroll
+        for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = x[j];
+        __syncwarp();
+        const int gc = gc0 + c0 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int grj = un.ti * S_BM + quad * 32 + j;
+          const float y = scr[j * 33 + lane];
+          if (grj < n && gc < n && (!diag || gc >= grj)) S[static_cast<size_t>(grj) * n + gc] = y;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tmem_empty[acc]);
+        mbar_arrive(&norm_empty[acc]);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_ph ^= 1u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S_TMEM_COLS);
+  }
+}
+
+}  // namespace ss
+
+using namespace ss;
+
+extern "C" int ss_segmented_plan128_host(const int32_t* offsets_host, int n_docs, int32_t* units_host, int64_t capacity_units,
+                                         int64_t* total_units) {
+  if (!offsets_host || n_docs < 0) return fail(SS_ERR_INVALID_ARG, "ss_segmented_plan128_host: bad arguments");
+  int64_t t = 0;
+  for (int d = 0; d < n_docs; ++d) {
+    const int64_t n = static_cast<int64_t>(offsets_host[d + 1]) - offsets_host[d];
+    if (n < 0) return fail(SS_ERR_INVALID_ARG, "ss_segmented_plan128_host: offsets must be non-decreasing");
+    const int T = static_cast<int>((n + S_BM - 1) / S_BM);
+    for (int ti = 0; ti < T; ++ti) {
+      for (int tj = ti; tj < T; ++tj) {
+        if (units_host) {
+          if (t >= capacity_units) return fail(SS_ERR_WORKSPACE, "ss_segmented_plan128_host: unit table too small");
+          units_host[4 * t + 0] = d;
+          units_host[4 * t + 1] = ti;
+          units_host[4 * t + 2] = tj;
+          units_host[4 * t + 3] = 0;
+        }
+        ++t;
+      }
+    }
+  }
+  if (total_units) *total_units = t;
+  return SS_OK;
+}
+
+extern "C" int ss_segmented_simmatrix_tc(const float* rows, int64_t total_rows, int dim, const int32_t* offsets,
+                                         const int64_t* s_offsets, const int32_t* units, int64_t n_units, float* out_S,
+                                         void* stream) {
+  if (!rows || !offsets || !s_offsets || !units || !out_S) return fail(SS_ERR_INVALID_ARG, "ss_segmented_simmatrix_tc: null pointer");
+  if (dim <= 0 || total_rows <= 0 || n_units < 0) return fail(SS_ERR_INVALID_ARG, "ss_segmented_simmatrix_tc: bad sizes");
+  if (n_units == 0) return SS_OK;
+  if ((dim & 3) != 0 || (reinterpret_cast<uintptr_t>(rows) & 15) != 0)
+    return fail(SS_ERR_UNSUPPORTED, "ss_segmented_simmatrix_tc: rows must be 16-byte multiples and 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(units) & 15) != 0) return fail(SS_ERR_INVALID_ARG, "ss_segmented_simmatrix_tc: unit table must be 16-byte aligned");
+  if (total_rows > 0x7FFFFFFFll - S_BM) return fail(SS_ERR_UNSUPPORTED, "ss_segmented_simmatrix_tc: too many rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tmap;
+  if (!make_tmap_rows(&tmap, rows, SS_F32, total_rows, dim, S_BM))
+    return fail(SS_ERR_CUDA, "ss_segmented_simmatrix_tc: cuTensorMapEncodeTiled failed");
+  SimTcParams p;
+  p.offsets = offsets;
+  p.s_offsets = reinterpret_cast<const long long*>(s_offsets);
+  p.units = reinterpret_cast<const int4*>(units);
+  p.n_units = n_units;
+  p.dim = dim;
+  p.nkb = (dim + S_BK - 1) / S_BK;
+  p.out = out_S;
+  const size_t smem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + 4 * 32 * 33 * 4 + 2 * 256 * 4 + 256;
+  cudaError_t e = cudaFuncSetAttribute(segmented_simmatrix_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e == cudaSuccess) {
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(sm_count(), n_units)));
+    ProfileScope prof(st);
+    segmented_simmatrix_tc_kernel<<<grid, S_THREADS, smem, st>>>(tmap, p);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "segmented_simmatrix_tc launch");
+  return SS_OK;
+}

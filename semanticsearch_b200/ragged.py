@@ -27,6 +27,7 @@ class RaggedPlan:
     offsets_d: torch.Tensor
     s_offsets_d: torch.Tensor
     tile_prefix_d: torch.Tensor
+    units128_d: Optional[torch.Tensor] = None   # int32 [units, 4] work list of the tensor-core kernel (built on first use)
 
     @property
     def n_docs(self) -> int:
@@ -67,19 +68,49 @@ def make_plan(sizes: Sequence[int], device) -> RaggedPlan:
                       torch.from_numpy(tile_prefix).to(dev))
 
 
-def segmented_simmatrix(E: torch.Tensor, plan: RaggedPlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """All per-document ``S = En @ En.T`` blocks, packed (Method/semantic_common.py:158-191)."""
+def _units128(plan: RaggedPlan, dev) -> torch.Tensor:
+    """Work list {doc, tile row, tile col, 0} of 128 x 128 upper-triangular tiles, uploaded once per plan."""
+    if plan.units128_d is None or plan.units128_d.device != dev:
+        lib = _lib.load()
+        total = ctypes.c_int64()
+        _lib.check(lib.ss_segmented_plan128_host(plan.offsets.ctypes.data, plan.n_docs, None, 0, ctypes.byref(total)),
+                   "ss_segmented_plan128_host")
+        units = np.zeros((max(int(total.value), 1), 4), dtype=np.int32)
+        _lib.check(lib.ss_segmented_plan128_host(plan.offsets.ctypes.data, plan.n_docs, units.ctypes.data, int(total.value),
+                                                 ctypes.byref(total)), "ss_segmented_plan128_host")
+        plan.units128_d = torch.from_numpy(units[: int(total.value)]).to(dev)
+    return plan.units128_d
+
+
+def segmented_simmatrix(E: torch.Tensor, plan: RaggedPlan, out: Optional[torch.Tensor] = None, algo: str = "auto") -> torch.Tensor:
+    """All per-document ``S = En @ En.T`` blocks, packed (Method/semantic_common.py:158-191).
+
+    ``algo``: "tc" = tcgen05 3xTF32 kernel (needs dim % 4 == 0), "ffma" = CUDA-core fp32 kernel,
+    "auto" = "tc" whenever its layout constraints hold."""
     dev = _require_cuda(E)
     if E.dtype != torch.float32 or E.dim() != 2 or not E.is_contiguous():
         raise ValueError("E must be a contiguous float32 [total_rows, dim] tensor")
     if E.shape[0] != plan.total_rows:
         raise ValueError(f"E has {E.shape[0]} rows, plan expects {plan.total_rows}")
+    if algo not in ("auto", "tc", "ffma"):
+        raise ValueError("algo must be 'auto', 'tc' or 'ffma'")
+    tc_ok = E.shape[1] % 4 == 0 and E.data_ptr() % 16 == 0 and plan.total_rows > 0
+    if algo == "tc" and not tc_ok:
+        raise ValueError("the tensor-core similarity kernel needs dim % 4 == 0 and 16-byte aligned rows")
+    use_tc = tc_ok if algo == "auto" else algo == "tc"
     lib = _lib.load()
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty(plan.total_s, dtype=torch.float32, device=dev)
         elif out.numel() < plan.total_s or out.dtype != torch.float32 or not out.is_cuda:
             raise ValueError("out must be a CUDA float32 tensor with at least plan.total_s elements")
+        if use_tc:
+            units = _units128(plan, dev)
+            st = lib.ss_segmented_simmatrix_tc(E.data_ptr(), E.shape[0], E.shape[1], plan.offsets_d.data_ptr(),
+                                               plan.s_offsets_d.data_ptr(), units.data_ptr(), units.shape[0], out.data_ptr(),
+                                               _stream_ptr(dev))
+            _lib.check(st, "ss_segmented_simmatrix_tc")
+            return out
         st = lib.ss_segmented_simmatrix(E.data_ptr(), E.shape[1], plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(),
                                         plan.tile_prefix_d.data_ptr(), plan.n_docs, plan.total_tiles, out.data_ptr(),
                                         _stream_ptr(dev))

@@ -1,0 +1,90 @@
+"""GPU parity tests for the tensor-core form of K3 (tcgen05 kind::tf32 with hi/lo operand splitting).
+
+Oracle: create_similarity_matrix's arithmetic (Method/semantic_common.py:158-164,186-191) restated in
+numpy (oracle/simmatrix_oracle.py) and an fp64 recomputation.  Tolerance 1e-5 abs (BASELINE.json
+north_star, fp32 inputs); the measured error of the 3xTF32 product must stay below 6e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import simmatrix_oracle as so
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _docs(rng, sizes, d, noise=0.7):
+    rows = []
+    for n in sizes:
+        n_topics = max(1, (n + 11) // 12)
+        cent = rng.standard_normal((n_topics, d)).astype(np.float32)
+        topic = np.minimum(np.arange(n) // 12, n_topics - 1)
+        rows.append((cent[topic] + noise * rng.standard_normal((n, d)).astype(np.float32)).astype(np.float32))
+    return rows
+
+
+def _run(rows_list, algo):
+    from semanticsearch_b200 import ragged
+    sizes = [r.shape[0] for r in rows_list]
+    E = np.concatenate([r for r in rows_list if r.shape[0] > 0], axis=0)
+    plan = ragged.make_plan(sizes, "cuda")
+    S = ragged.segmented_simmatrix(torch.from_numpy(E).cuda(), plan, algo=algo)
+    torch.cuda.synchronize()
+    S_host = S.cpu().numpy()
+    return [S_host[plan.s_offsets[i]:plan.s_offsets[i + 1]].reshape(sizes[i], sizes[i]) for i in range(len(sizes))]
+
+
+def _fp64(E):
+    E = E.astype(np.float64)
+    nrm = np.linalg.norm(E, axis=1, keepdims=True)
+    nrm[nrm == 0] = 1e-9
+    En = E / nrm
+    return En @ En.T
+
+
+@pytest.mark.parametrize("d", [768, 384, 100, 4])
+def test_tc_ragged_batch_vs_oracle(d):
+    rng = np.random.default_rng(30 + d)
+    sizes = [int(x) for x in rng.integers(16, 513, size=24)] + [1, 2, 0, 64, 65, 127, 128, 129, 256, 257, 511, 512, 513, 700]
+    rows = _docs(rng, sizes, d)
+    blocks = _run(rows, "tc")
+    worst = 0.0
+    for E, S in zip(rows, blocks):
+        if E.shape[0] == 0:
+            continue
+        np.testing.assert_array_equal(S, S.T)                     # exactly symmetric
+        if E.shape[0] >= 2:
+            np.testing.assert_allclose(S, so.similarity_matrix_ref(E), atol=TOL, rtol=0)
+        worst = max(worst, float(np.abs(S - _fp64(E)).max()))
+    print(f"d={d}: max |S - S_fp64| = {worst:.3e}")
+    assert worst < 6e-6, worst
+
+
+def test_tc_matches_ffma_kernel_and_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "grouping.npz"))
+    for name in ("a", "b", "c", "tiny", "seven"):
+        E = g[f"{name}_E"]
+        S_tc = _run([E], "tc")[0]
+        S_ff = _run([E], "ffma")[0]
+        np.testing.assert_allclose(S_tc, g[f"{name}_S"], atol=TOL, rtol=0)   # the reference's own output
+        np.testing.assert_allclose(S_tc, S_ff, atol=6e-6, rtol=0)
+    S = _run([g["a_E"]], "tc")[0]
+    assert np.all(S[5] == 0) and np.all(S[:, 5] == 0)  # zero sentence vector -> zero row/column
+
+
+def test_tc_adversarial_magnitudes():
+    """Rows scaled over 12 orders of magnitude and near-duplicate rows: the hi/lo split must stay relative."""
+    rng = np.random.default_rng(77)
+    n, d = 300, 768
+    E = rng.standard_normal((n, d)).astype(np.float32)
+    E *= (10.0 ** rng.uniform(-6, 6, size=(n, 1))).astype(np.float32)
+    E[10] = E[3] * np.float32(1.0000001)
+    E[11] = -E[3]
+    E[12] = 0
+    S = _run([E], "tc")[0]
+    np.testing.assert_allclose(S, _fp64(E), atol=TOL, rtol=0)
+    assert abs(S[3, 10] - 1.0) < 6e-6 and abs(S[3, 11] + 1.0) < 6e-6
+    assert np.all(S[12] == 0)
