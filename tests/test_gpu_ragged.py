@@ -108,7 +108,7 @@ def test_group_pass_selection_logic_is_exact():
     """Quantiles and neighbour lists must equal numpy's on the kernel's own sim_sharp, bit for bit."""
     from semanticsearch_b200 import ragged
     rng = np.random.default_rng(17)
-    sizes = [16, 17, 33, 100, 257, 512, 2, 3, 64, 300]
+    sizes = [16, 17, 33, 100, 257, 512, 2, 3, 64, 300, 513, 700]  # > 512 rows: the generic (memory-resident) row path
     rows = topic_docs(rng, sizes, 96)
     rows[3][7] = 0.0
     plan, _, S, blocks = run_sim(rows)
