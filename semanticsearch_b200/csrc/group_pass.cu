@@ -61,8 +61,8 @@ __device__ __forceinline__ double np_lerp(double a, double b, double g) {
   return r;
 }
 
-constexpr int kRowRegs = 16;               // fast path: a whole row (n <= 512) lives in 16 registers per lane
-constexpr int kFastMaxN = 32 * kRowRegs;
+constexpr int kFastMaxN = 512;  // fast path: a whole row lives in 4..16 registers per lane
+constexpr int kListCap = 2048;  // candidates per quantile the shared-memory selection can hold
 
 // One warp sorts a[0..64) (shared memory) in descending order.
 __device__ __forceinline__ void warp_bitonic64_desc(uint64_t* a, int lane) {
@@ -91,12 +91,206 @@ __device__ __forceinline__ void hist_add_aggregated(unsigned int* hist, unsigned
   if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], static_cast<unsigned int>(__popc(peers)));
 }
 
+// One warp walks a histogram to the bin that holds 0-based rank `want`: returns the bin, the rank
+// inside it and its population (all lanes get the result).
+__device__ __forceinline__ void walk_hist(const unsigned int* h, int nb, unsigned int want, int lane, unsigned int& bin,
+                                          unsigned int& rank_in, unsigned int& count) {
+  unsigned int run = 0u;
+  bin = 0u;
+  rank_in = 0u;
+  count = 0u;
+  for (int b0 = 0; b0 < nb; b0 += 32) {
+    const unsigned int c = h[b0 + lane];
+    unsigned int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const unsigned int excl = run + incl - c;
+    const bool here = (want >= excl) && (want < excl + c);
+    const unsigned int bal = __ballot_sync(0xffffffffu, here);
+    if (bal) {
+      const int src = __ffs(bal) - 1;
+      bin = static_cast<unsigned int>(b0 + src);
+      rank_in = want - __shfl_sync(0xffffffffu, excl, src);
+      count = __shfl_sync(0xffffffffu, c, src);
+      return;
+    }
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// All threads of the block sort a[0..n) (n a power of two, shared memory) in ascending order.
+__device__ __forceinline__ void block_bitonic_asc_u32(unsigned int* a, int n) {
+  for (int k2 = 2; k2 <= n; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int q = i | j;
+        const unsigned int x = a[i], y = a[q];
+        const bool asc = (i & k2) == 0;
+        if (asc ? (x > y) : (x < y)) {
+          a[i] = y;
+          a[q] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct RowCtx {
+  const float* S;
+  float* sharp;
+  int n, row_base, width;
+  float mu, sigma, tau;
+  unsigned int* hist;  // linear-bin histogram of the positive sharpened values
+  uint64_t* scr;       // this warp's 64-key scratch
+  double* centrality;
+  int* knn_idx;
+  float* knn_val;
+};
+
+// Monotone 2048-way binning of a sharpened value in (0, 1]: exact (power-of-two scale + truncation).
+__device__ __forceinline__ unsigned int lin_bin(float v) { return min(2047u, static_cast<unsigned int>(v * 2048.0f)); }
+
+// One warp per row with the row held in NREG registers per lane (n <= 32 * NREG).
+template <int NREG>
+__device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int lane, double& pos_s1, double& pos_s2,
+                                              unsigned int& pos_cnt) {
+  const float* S = cx.S;
+  float* sharp = cx.sharp;
+  const int n = cx.n, row_base = cx.row_base, width = cx.width;
+  const float mu = cx.mu;
+  const float zscale = 1.4426950408889634f / (cx.sigma * cx.tau);  // log2(e) / (sigma * tau)
+  uint64_t* scr = cx.scr;
+    for (int r = warp; r < n; r += kGrpWarps) {
+      const float* srow = S + static_cast<size_t>(r) * n;
+      float* orow = sharp + static_cast<size_t>(r) * n;
+      uint32_t o[NREG];  // order-preserving bits of the sharpened value; 0 = column past the end
+      double rs = 0.0;
+#pragma unroll
+      for (int j = 0; j < NREG; ++j) {
+        o[j] = 0u;
+        if (32 * j < n) {
+          const int c = lane + 32 * j;
+          bool pos = false;
+          unsigned int bits = 0u;
+          if (c < n) {
+            // sigmoid(((S - mu) / sigma) / tau) with one FMA, ex2.approx and rcp.approx: a few ulp from
+            // the reference's fp32 expression (Grouping:105-106), far inside the 1e-5 bound; saturates
+            // to exactly 0 / 1 like numpy's exp overflow does
+            float v = __frcp_rn(1.0f + exp2f(-((srow[c] - mu) * zscale)));
+            if (c == r) v = 0.f;
+            orow[c] = v;
+            rs += static_cast<double>(v);
+            o[j] = float_to_ordered(v);
+            if (v > 0.f) {
+              pos = true;
+              bits = __float_as_uint(v);
+              pos_s1 += static_cast<double>(v);
+              pos_s2 += static_cast<double>(v) * static_cast<double>(v);
+              ++pos_cnt;
+            }
+          }
+          hist_add_aggregated(cx.hist, lin_bin(__uint_as_float(bits)), pos, lane);
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+      if (lane == 0) {
+        const float rsum = static_cast<float>(rs);
+        cx.centrality[row_base + r] = static_cast<double>(rsum / static_cast<float>(max(n - 1, 1)));
+      }
+      // top-`width` of the row (value desc, index asc).  Cheap bound first: each lane's two largest values
+      // form a 64-value sample; its width-th largest L is a lower bound of the row's width-th largest, and
+      // usually only a few more than `width` columns reach L — gather those and sort them.
+      scr[lane] = 0ull;
+      scr[lane + 32] = 0ull;
+      const unsigned int lt_mask = (1u << lane) - 1u;
+      uint32_t m1 = 0u, m2 = 0u;
+#pragma unroll
+      for (int j = 0; j < NREG; ++j) {
+        m2 = max(m2, min(m1, o[j]));
+        m1 = max(m1, o[j]);
+      }
+      uint32_t L = 0x80000000u;  // every real column has bit 31 set
+#pragma unroll 1
+      for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t cand = L | (1u << bit);
+        const int c = __reduce_add_sync(0xffffffffu, (m1 >= cand ? 1 : 0) + (m2 >= cand ? 1 : 0));
+        if (c >= width) L = cand;
+      }
+      int c_ge = 0;
+#pragma unroll
+      for (int j = 0; j < NREG; ++j) c_ge += (o[j] >= L) ? 1 : 0;
+      c_ge = __reduce_add_sync(0xffffffffu, c_ge);
+      __syncwarp();
+      if (c_ge <= 64) {
+        int base = 0;
+#pragma unroll
+        for (int j = 0; j < NREG; ++j) {
+          if (32 * j < n) {
+            const unsigned int m_ge = __ballot_sync(0xffffffffu, o[j] >= L);
+            if (o[j] >= L)
+              scr[base + __popc(m_ge & lt_mask)] = (static_cast<uint64_t>(o[j]) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(lane + 32 * j));
+            base += __popc(m_ge);
+          }
+        }
+      } else {
+        // crowded (many ties at the bound): the width-th largest value T by bisection over the whole row,
+        // then everything above T plus the lowest-index ties
+        uint32_t T = 0x80000000u;
+#pragma unroll 1
+        for (int bit = 30; bit >= 0; --bit) {
+          const uint32_t cand = T | (1u << bit);
+          int c = 0;
+#pragma unroll
+          for (int j = 0; j < NREG; ++j) c += (o[j] >= cand) ? 1 : 0;
+          c = __reduce_add_sync(0xffffffffu, c);
+          if (c >= width) T = cand;
+        }
+        int c_gt = 0;
+#pragma unroll
+        for (int j = 0; j < NREG; ++j) c_gt += (o[j] > T) ? 1 : 0;
+        c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+        int base_gt = 0, taken_eq = 0;
+#pragma unroll
+        for (int j = 0; j < NREG; ++j) {
+          if (32 * j < n) {
+            const uint64_t key = (static_cast<uint64_t>(o[j]) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(lane + 32 * j));
+            const unsigned int m_gt = __ballot_sync(0xffffffffu, o[j] > T);
+            const unsigned int m_eq = __ballot_sync(0xffffffffu, o[j] == T);
+            if (o[j] > T) scr[base_gt + __popc(m_gt & lt_mask)] = key;
+            base_gt += __popc(m_gt);
+            const int room = width - c_gt - taken_eq;  // ties are admitted in ascending column order
+            const int my_rank = __popc(m_eq & lt_mask);
+            if (o[j] == T && my_rank < room) scr[c_gt + taken_eq + my_rank] = key;
+            taken_eq += min(__popc(m_eq), max(room, 0));
+          }
+        }
+      }
+      __syncwarp();
+      warp_bitonic64_desc(scr, lane);
+      int* oi = cx.knn_idx + static_cast<size_t>(row_base + r) * kKnnWidth;
+      float* ov = cx.knn_val + static_cast<size_t>(row_base + r) * kKnnWidth;
+      for (int s = lane; s < kKnnWidth; s += 32) {
+        const uint64_t key = scr[s];
+        const bool ok = s < width;
+        oi[s] = ok ? static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull)) : -1;
+        ov[s] = ok ? ordered_to_float(static_cast<uint32_t>(key >> 32)) : 0.f;
+      }
+      __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const GroupParams p) {
   __shared__ double red[kGrpWarps];
   __shared__ unsigned int hist[kNumQ][kRadixBins];
   __shared__ uint64_t knn_scr[kGrpWarps][64];
   __shared__ unsigned int t_prefix[kNumQ], t_rank[kNumQ];  // per target: determined high bits, remaining rank
-  __shared__ unsigned int t_cnt_le[kNumQ], t_min_above[kNumQ];
+  __shared__ unsigned int t_cnt_le[kNumQ], t_min_above[kNumQ], t_fill[kNumQ];
   __shared__ float s_mu, s_sigma;
 
   const int doc = blockIdx.x;
@@ -144,90 +338,14 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
   unsigned int pos_cnt = 0;
   if (n <= kFastMaxN) {
     // Fast path: one warp per row, the row stays in registers for all four products of the pass.
-    uint64_t* scr = knn_scr[warp];
-    for (int r = warp; r < n; r += kGrpWarps) {
-      const float* srow = S + static_cast<size_t>(r) * n;
-      float* orow = sharp + static_cast<size_t>(r) * n;
-      uint32_t o[kRowRegs];  // order-preserving bits of the sharpened value; 0 = column past the end
-      double rs = 0.0;
-#pragma unroll
-      for (int j = 0; j < kRowRegs; ++j) {
-        o[j] = 0u;
-        if (32 * j < n) {
-          const int c = lane + 32 * j;
-          bool pos = false;
-          unsigned int bits = 0u;
-          if (c < n) {
-            const float z = (srow[c] - mu) / sigma;
-            float v = 1.0f / (1.0f + expf(-(z / tau)));
-            if (c == r) v = 0.f;
-            orow[c] = v;
-            rs += static_cast<double>(v);
-            o[j] = float_to_ordered(v);
-            if (v > 0.f) {
-              pos = true;
-              bits = __float_as_uint(v);
-              pos_s1 += static_cast<double>(v);
-              pos_s2 += static_cast<double>(v) * static_cast<double>(v);
-              ++pos_cnt;
-            }
-          }
-          hist_add_aggregated(hist[0], bits >> 21, pos, lane);
-        }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
-      if (lane == 0) {
-        const float rsum = static_cast<float>(rs);
-        p.centrality[row_base + r] = static_cast<double>(rsum / static_cast<float>(max(n - 1, 1)));
-      }
-      // top-`width` of the row (value desc, index asc): the width-th largest value T by bisection on the
-      // ordered bits (every real column has bit 31 set), then everything above T plus the lowest-index ties
-      uint32_t T = 0x80000000u;
-#pragma unroll 1
-      for (int bit = 30; bit >= 0; --bit) {
-        const uint32_t cand = T | (1u << bit);
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < kRowRegs; ++j) c += (o[j] >= cand) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= width) T = cand;
-      }
-      int c_gt = 0;
-#pragma unroll
-      for (int j = 0; j < kRowRegs; ++j) c_gt += (o[j] > T) ? 1 : 0;
-      c_gt = __reduce_add_sync(0xffffffffu, c_gt);
-      scr[lane] = 0ull;
-      scr[lane + 32] = 0ull;
-      __syncwarp();
-      int base_gt = 0, taken_eq = 0;
-      const unsigned int lt_mask = (1u << lane) - 1u;
-#pragma unroll
-      for (int j = 0; j < kRowRegs; ++j) {
-        if (32 * j < n) {
-          const uint64_t key = (static_cast<uint64_t>(o[j]) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(lane + 32 * j));
-          const unsigned int m_gt = __ballot_sync(0xffffffffu, o[j] > T);
-          const unsigned int m_eq = __ballot_sync(0xffffffffu, o[j] == T);
-          if (o[j] > T) scr[base_gt + __popc(m_gt & lt_mask)] = key;
-          base_gt += __popc(m_gt);
-          const int room = width - c_gt - taken_eq;  // ties are admitted in ascending column order
-          const int my_rank = __popc(m_eq & lt_mask);
-          if (o[j] == T && my_rank < room) scr[c_gt + taken_eq + my_rank] = key;
-          taken_eq += min(__popc(m_eq), max(room, 0));
-        }
-      }
-      __syncwarp();
-      warp_bitonic64_desc(scr, lane);
-      int* oi = p.knn_idx + static_cast<size_t>(row_base + r) * kKnnWidth;
-      float* ov = p.knn_val + static_cast<size_t>(row_base + r) * kKnnWidth;
-      for (int s = lane; s < kKnnWidth; s += 32) {
-        const uint64_t key = scr[s];
-        const bool ok = s < width;
-        oi[s] = ok ? static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull)) : -1;
-        ov[s] = ok ? ordered_to_float(static_cast<uint32_t>(key >> 32)) : 0.f;
-      }
-      __syncwarp();
-    }
+    RowCtx cx;
+    cx.S = S; cx.sharp = sharp; cx.n = n; cx.row_base = row_base; cx.width = width;
+    cx.mu = mu; cx.sigma = sigma; cx.tau = tau; cx.hist = hist[0]; cx.scr = knn_scr[warp];
+    cx.centrality = p.centrality; cx.knn_idx = p.knn_idx; cx.knn_val = p.knn_val;
+    if (n <= 128) row_pass_regs<4>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    else if (n <= 256) row_pass_regs<8>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    else if (n <= 384) row_pass_regs<12>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    else row_pass_regs<16>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
   } else {
     // Generic path for very long documents: rows are re-read from memory.
     for (int r = warp; r < n; r += kGrpWarps) {
@@ -252,7 +370,7 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
             ++pos_cnt;
           }
         }
-        hist_add_aggregated(hist[0], bits >> 21, pos, lane);
+        hist_add_aggregated(hist[0], lin_bin(__uint_as_float(bits)), pos, lane);
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
@@ -306,98 +424,144 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
   }
   double q_out[kNumQ] = {0.0, 0.0, 0.0};
   if (m > 0) {
-    if (tid < kNumQ) {
-      t_prefix[tid] = 0u;
-      t_rank[tid] = lo_rank[tid];
+    // 3a. walk the linear-bin histogram: bin, rank inside the bin and population of the bin per target
+    if (warp < kNumQ) {
+      unsigned int bin, rin, cnt;
+      walk_hist(hist[0], kRadixBins, lo_rank[warp], lane, bin, rin, cnt);
+      if (lane == 0) {
+        t_prefix[warp] = bin;
+        t_rank[warp] = rin;
+        t_cnt_le[warp] = cnt;
+        t_min_above[warp] = 0xFFFFFFFFu;
+      }
     }
-    const int shifts[3] = {21, 10, 0};
-    const int widths[3] = {11, 11, 10};
-    unsigned int known_mask = 0u;
-    for (int pass = 0; pass < 3; ++pass) {
-      const int sh = shifts[pass];
-      const unsigned int dmask = (1u << widths[pass]) - 1u;
-      if (pass > 0) {
+    __syncthreads();
+    const unsigned int b0 = t_prefix[0], b1 = t_prefix[1], b2 = t_prefix[2];
+    const unsigned int n0 = t_cnt_le[0], n1 = t_cnt_le[1], n2 = t_cnt_le[2];
+    if (n0 <= kListCap && n1 <= kListCap && n2 <= kListCap) {
+      // 3b. fast path: ONE more pass over sim_sharp gathers each target bin's values into shared memory
+      // (the histogram is dead now and becomes the three lists) and tracks the smallest value above each bin
+      unsigned int* lists = &hist[0][0];
+      __syncthreads();
+      if (tid < kNumQ) t_fill[tid] = 0u;
+      __syncthreads();
+      unsigned int a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
+      for (long long i0 = 0; i0 < nn; i0 += 4 * kGrpThreads) {
+        unsigned int bb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const long long i = i0 + q * kGrpThreads + tid;
+          bb[q] = i < nn ? __float_as_uint(sharp[i]) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned int b = bb[q];
+          if (b == 0u) continue;  // diagonal / underflowed zeros are not "positive values"
+          const unsigned int bin = lin_bin(__uint_as_float(b));
+          if (bin == b0) lists[atomicAdd(&t_fill[0], 1u)] = b; else if (bin > b0) a0 = min(a0, b);
+          if (bin == b1) lists[kListCap + atomicAdd(&t_fill[1], 1u)] = b; else if (bin > b1) a1 = min(a1, b);
+          if (bin == b2) lists[2 * kListCap + atomicAdd(&t_fill[2], 1u)] = b; else if (bin > b2) a2 = min(a2, b);
+        }
+      }
+      a0 = __reduce_min_sync(0xffffffffu, a0);
+      a1 = __reduce_min_sync(0xffffffffu, a1);
+      a2 = __reduce_min_sync(0xffffffffu, a2);
+      if (lane == 0) {
+        atomicMin(&t_min_above[0], a0);
+        atomicMin(&t_min_above[1], a1);
+        atomicMin(&t_min_above[2], a2);
+      }
+      __syncthreads();
+      // 3c. sort each list (positive floats order like their bit patterns) and read the two order statistics
+#pragma unroll 1
+      for (int t = 0; t < kNumQ; ++t) {
+        const unsigned int cnt = t_cnt_le[t];
+        unsigned int* l = lists + t * kListCap;
+        int np2 = 2;
+        while (np2 < static_cast<int>(cnt)) np2 <<= 1;
+        for (int i = static_cast<int>(cnt) + tid; i < np2; i += kGrpThreads) l[i] = 0xFFFFFFFFu;
+        __syncthreads();
+        block_bitonic_asc_u32(l, np2);
+        const unsigned int rin = t_rank[t];
+        const unsigned int vlo = l[rin];
+        unsigned int vhi = vlo;
+        if (lo_rank[t] + 1 < m) vhi = (rin + 1 < cnt) ? l[rin + 1] : t_min_above[t];
+        q_out[t] = np_lerp(static_cast<double>(__uint_as_float(vlo)), static_cast<double>(__uint_as_float(vhi)), gamma[t]);
+      }
+    } else {
+      // 3d. fallback (a bin too crowded for shared memory, e.g. thousands of identical similarities):
+      // 3-pass (11/11/10-bit) radix select on the fp32 bit patterns, every pass re-reading sim_sharp
+      __syncthreads();
+      if (tid < kNumQ) {
+        t_prefix[tid] = 0u;
+        t_rank[tid] = lo_rank[tid];
+      }
+      const int shifts[3] = {21, 10, 0};
+      const int widths[3] = {11, 11, 10};
+      unsigned int known_mask = 0u;
+      for (int pass = 0; pass < 3; ++pass) {
+        const int sh = shifts[pass];
+        const unsigned int dmask = (1u << widths[pass]) - 1u;
         for (int i = tid; i < kNumQ * kRadixBins; i += kGrpThreads) (&hist[0][0])[i] = 0u;
         __syncthreads();
         const unsigned int pf0 = t_prefix[0], pf1 = t_prefix[1], pf2 = t_prefix[2];
-        for (long long i = tid; i < nn; i += kGrpThreads) {
-          const unsigned int b = __float_as_uint(sharp[i]);
-          if (b == 0u) continue;  // diagonal / underflowed zeros are not "positive values"
+        for (long long i0 = 0; i0 < nn; i0 += kGrpThreads) {  // warp-uniform trip count: the aggregation needs all lanes
+          const long long i = i0 + tid;
+          const unsigned int b = i < nn ? __float_as_uint(sharp[i]) : 0u;
           const unsigned int hi = b & known_mask, dg = (b >> sh) & dmask;
-          if (hi == pf0) atomicAdd(&hist[0][dg], 1u);
-          if (hi == pf1) atomicAdd(&hist[1][dg], 1u);
-          if (hi == pf2) atomicAdd(&hist[2][dg], 1u);
+          hist_add_aggregated(hist[0], dg, b != 0u && hi == pf0, lane);
+          hist_add_aggregated(hist[1], dg, b != 0u && hi == pf1, lane);
+          hist_add_aggregated(hist[2], dg, b != 0u && hi == pf2, lane);
         }
+        __syncthreads();
+        if (warp < kNumQ) {
+          unsigned int bin, rin, cnt;
+          walk_hist(hist[warp], 1 << widths[pass], t_rank[warp], lane, bin, rin, cnt);
+          if (lane == 0) {
+            t_prefix[warp] |= bin << sh;
+            t_rank[warp] = rin;
+          }
+        }
+        known_mask |= dmask << sh;
+        __syncthreads();
+      }
+      // upper order statistic: next distinct value unless duplicates already cover rank lo+1
+      if (tid < kNumQ) {
+        t_cnt_le[tid] = 0u;
+        t_min_above[tid] = 0xFFFFFFFFu;
       }
       __syncthreads();
-      // one warp per target walks its histogram (pass 0: the shared one) to the bin that holds the wanted rank
-      if (warp < kNumQ) {
-        const unsigned int* h = pass == 0 ? hist[0] : hist[warp];
-        const unsigned int want = t_rank[warp];
-        unsigned int run = 0u;
-        const int nb = 1 << widths[pass];
-        for (int b0 = 0; b0 < nb; b0 += 32) {
-          const unsigned int c = h[b0 + lane];
-          unsigned int incl = c;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-          }
-          const unsigned int excl = run + incl - c;
-          const bool here = (want >= excl) && (want < excl + c);
-          const unsigned int bal = __ballot_sync(0xffffffffu, here);
-          if (bal) {
-            const int src = __ffs(bal) - 1;
-            const unsigned int e = __shfl_sync(0xffffffffu, excl, src);
-            if (lane == 0) {
-              t_prefix[warp] |= static_cast<unsigned int>(b0 + src) << sh;
-              t_rank[warp] = want - e;
-            }
-            break;
-          }
-          run += __shfl_sync(0xffffffffu, incl, 31);
-        }
+      const unsigned int v0 = t_prefix[0], v1 = t_prefix[1], v2 = t_prefix[2];
+      unsigned int c0 = 0, c1 = 0, c2 = 0, a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
+      for (long long i = tid; i < nn; i += kGrpThreads) {
+        const unsigned int b = __float_as_uint(sharp[i]);
+        if (b == 0u) continue;
+        if (b <= v0) ++c0; else a0 = min(a0, b);
+        if (b <= v1) ++c1; else a1 = min(a1, b);
+        if (b <= v2) ++c2; else a2 = min(a2, b);
       }
-      known_mask |= dmask << sh;
+      c0 = __reduce_add_sync(0xffffffffu, c0);
+      c1 = __reduce_add_sync(0xffffffffu, c1);
+      c2 = __reduce_add_sync(0xffffffffu, c2);
+      a0 = __reduce_min_sync(0xffffffffu, a0);
+      a1 = __reduce_min_sync(0xffffffffu, a1);
+      a2 = __reduce_min_sync(0xffffffffu, a2);
+      if (lane == 0) {
+        atomicAdd(&t_cnt_le[0], c0);
+        atomicAdd(&t_cnt_le[1], c1);
+        atomicAdd(&t_cnt_le[2], c2);
+        atomicMin(&t_min_above[0], a0);
+        atomicMin(&t_min_above[1], a1);
+        atomicMin(&t_min_above[2], a2);
+      }
       __syncthreads();
-    }
-    // ---- upper order statistic: next distinct value unless duplicates already cover rank lo+1 ----
-    if (tid < kNumQ) {
-      t_cnt_le[tid] = 0u;
-      t_min_above[tid] = 0xFFFFFFFFu;
-    }
-    __syncthreads();
-    const unsigned int v0 = t_prefix[0], v1 = t_prefix[1], v2 = t_prefix[2];
-    unsigned int c0 = 0, c1 = 0, c2 = 0, a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
-    for (long long i = tid; i < nn; i += kGrpThreads) {
-      const unsigned int b = __float_as_uint(sharp[i]);
-      if (b == 0u) continue;
-      if (b <= v0) ++c0; else a0 = min(a0, b);
-      if (b <= v1) ++c1; else a1 = min(a1, b);
-      if (b <= v2) ++c2; else a2 = min(a2, b);
-    }
-    c0 = __reduce_add_sync(0xffffffffu, c0);
-    c1 = __reduce_add_sync(0xffffffffu, c1);
-    c2 = __reduce_add_sync(0xffffffffu, c2);
-    a0 = __reduce_min_sync(0xffffffffu, a0);
-    a1 = __reduce_min_sync(0xffffffffu, a1);
-    a2 = __reduce_min_sync(0xffffffffu, a2);
-    if (lane == 0) {
-      atomicAdd(&t_cnt_le[0], c0);
-      atomicAdd(&t_cnt_le[1], c1);
-      atomicAdd(&t_cnt_le[2], c2);
-      atomicMin(&t_min_above[0], a0);
-      atomicMin(&t_min_above[1], a1);
-      atomicMin(&t_min_above[2], a2);
-    }
-    __syncthreads();
 #pragma unroll
-    for (int t = 0; t < kNumQ; ++t) {
-      const unsigned int vlo = t_prefix[t];
-      unsigned int vhi = vlo;
-      if (lo_rank[t] + 1 < m && t_cnt_le[t] <= lo_rank[t] + 1) vhi = t_min_above[t];
-      q_out[t] = np_lerp(static_cast<double>(__uint_as_float(vlo)), static_cast<double>(__uint_as_float(vhi)), gamma[t]);
+      for (int t = 0; t < kNumQ; ++t) {
+        const unsigned int vlo = t_prefix[t];
+        unsigned int vhi = vlo;
+        if (lo_rank[t] + 1 < m && t_cnt_le[t] <= lo_rank[t] + 1) vhi = t_min_above[t];
+        q_out[t] = np_lerp(static_cast<double>(__uint_as_float(vlo)), static_cast<double>(__uint_as_float(vhi)), gamma[t]);
+      }
     }
   }
 

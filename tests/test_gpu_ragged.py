@@ -209,3 +209,41 @@ def test_splitter_other_percentiles_and_large_batch():
             t_ref, bp_ref = spo.p95_breakpoints_ref(mine, pct)
             assert thr[di] == t_ref
             np.testing.assert_array_equal(np.nonzero(flags[a:b])[0], bp_ref)
+
+
+def test_group_pass_crowded_bin_takes_radix_fallback():
+    """Thousands of identical similarities land in one histogram bin (more than the shared-memory
+    candidate list holds): the radix-select fallback must still return numpy's quantiles exactly."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(23)
+    sizes = [100, 80, 300]
+    mats = []
+    S0 = np.full((100, 100), 0.3, dtype=np.float32)
+    np.fill_diagonal(S0, 1.0)
+    mats.append(S0)                                   # 9900 identical off-diagonal values
+    S1 = np.where(rng.random((80, 80)) < 0.5, 0.2, 0.7).astype(np.float32)
+    S1 = np.maximum(S1, S1.T)
+    np.fill_diagonal(S1, 1.0)
+    mats.append(S1)                                   # two heavy clusters of duplicates
+    E = topic_docs(rng, [300], 64)[0]
+    mats.append(so.similarity_matrix_ref(E).astype(np.float32))  # ordinary document in the same batch
+    plan = ragged.make_plan(sizes, "cuda")
+    S = torch.from_numpy(np.concatenate([m.reshape(-1) for m in mats])).cuda()
+    out = ragged.group_threshold_pass(S, plan)
+    torch.cuda.synchronize()
+    sharp_all = out["sim_sharp"].cpu().numpy()
+    stats = out["doc_stats"].cpu().numpy()
+    kidx = out["knn_idx"].cpu().numpy()
+    kval = out["knn_val"].cpu().numpy()
+    for d, n in enumerate(sizes):
+        sharp = sharp_all[plan.s_offsets[d]:plan.s_offsets[d + 1]].reshape(n, n)
+        thr = go.thresholds_ref(sharp)
+        assert stats[d, 6] == thr["count"]
+        assert stats[d, 2] == thr["edge_floor"], (d, n)
+        assert stats[d, 3] == thr["tau_merge"]
+        assert stats[d, 4] == thr["global_merge_thr"]
+        idx_ref, val_ref = go.knn_lists_ref(sharp, go.k_eff_auto(n))
+        w = idx_ref.shape[1]
+        rows_d = slice(plan.offsets[d], plan.offsets[d + 1])
+        np.testing.assert_array_equal(kidx[rows_d, :w], idx_ref)   # ties -> ascending column index
+        np.testing.assert_array_equal(kval[rows_d, :w], val_ref)
