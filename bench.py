@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "queries/s top-10 cosine over 10M x 768 bf16 corpus"
+METRIC = "queries/s top-10 cosine over 10M x 768 bf16 corpus"  # BASELINE.json headline; other shapes rename it below
 UNIT = "queries/s"
 
 
@@ -42,9 +42,13 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="corpus/query storage type (BASELINE config 4: bf16; config 5: fp16 with --rows 100000000 --dim 384 --k 100 --batch 16)")
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--algo", default="auto", choices=["auto", "stream", "tcstream", "gemm"],
+                    help="force one kernel for the headline batch (experiments); auto = the library's dispatch")
     return ap.parse_args()
 
 
@@ -108,7 +112,7 @@ def run_reference(args):
         return
     base, dt = cpu_reference_qps(args, steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup > 0 else 0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args), "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
@@ -119,8 +123,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def metric_name(args):
+    if (args.rows, args.dim, args.k, args.dtype) == (10_000_000, 768, 10, "bf16"):
+        return METRIC
+    return f"queries/s top-{args.k} cosine over {args.rows} x {args.dim} {args.dtype} corpus"
+
+
 def workload_config(args):
-    return {"workload": f"cfg4: brute-force top-{args.k} cosine, {args.rows}x{args.dim} bf16 corpus (not pre-normalised), "
+    tag = "cfg4" if (args.dim, args.k, args.dtype) == (768, 10, "bf16") else ("cfg5" if (args.dim, args.k, args.dtype) == (384, 100, "fp16") else "custom")
+    return {"workload": f"{tag}: brute-force top-{args.k} cosine, {args.rows}x{args.dim} {args.dtype} corpus (not pre-normalised), "
                         f"query batch {args.batch}",
             "rows": args.rows, "dim": args.dim, "k": args.k, "query_batch": args.batch,
             "sharding": f"corpus rows split {args.gpus}-way, queries replicated, all-gather of top-k keys",
@@ -183,14 +194,14 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
-def make_shard(rows, dim, seed, device):
+def make_shard(rows, dim, seed, device, dtype):
     import torch
-    out = torch.empty((rows, dim), dtype=torch.bfloat16, device=device)
+    out = torch.empty((rows, dim), dtype=dtype, device=device)
     g = torch.Generator(device=device).manual_seed(seed)
     step = 1 << 20
     for a in range(0, rows, step):
         b = min(rows, a + step)
-        out[a:b] = torch.randn((b - a, dim), generator=g, device=device, dtype=torch.float32).to(torch.bfloat16)
+        out[a:b] = torch.randn((b - a, dim), generator=g, device=device, dtype=torch.float32).to(dtype)
     return out
 
 
@@ -213,9 +224,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     lo, hi = shard_bounds(args.rows, world, rank)
-    shard = make_shard(hi - lo, args.dim, 6 + rank, dev)
+    tdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    shard = make_shard(hi - lo, args.dim, 6 + rank, dev, tdtype)
     corpus = ShardedCorpus(shard, lo)
     q_host = q_dev = out_s_host = out_i_host = None
+    cur_algo = [args.algo]
     lib = _lib.load()
 
     def barrier():
@@ -224,11 +237,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_resident():
-        return corpus.search(q_dev, args.k)
+        return corpus.search(q_dev, args.k, algo=cur_algo[0])
 
     def step_e2e():
         q = q_host.to(dev, non_blocking=True)
-        s, i = corpus.search(q, args.k)
+        s, i = corpus.search(q, args.k, algo=cur_algo[0])
         out_s_host.copy_(s, non_blocking=True)
         out_i_host.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the result every step
@@ -260,7 +273,7 @@ def run_ours(args):
         """Device-resident and end-to-end timing of `steps` searches with a batch of `batch` queries."""
         nonlocal q_host, q_dev, out_s_host, out_i_host
         gq = torch.Generator(device="cpu").manual_seed(7 if batch == 1 else 8)
-        q_host = torch.randn((batch, args.dim), generator=gq, dtype=torch.float32).to(torch.bfloat16).pin_memory()
+        q_host = torch.randn((batch, args.dim), generator=gq, dtype=torch.float32).to(tdtype).pin_memory()
         q_dev = q_host.to(dev)
         out_s_host = torch.empty((batch, args.k), dtype=torch.float32).pin_memory()
         out_i_host = torch.empty((batch, args.k), dtype=torch.int64).pin_memory()
@@ -282,7 +295,7 @@ def run_ours(args):
         hbm_peak, tf_peak, tf_sustained, peak_src = peaks()
         qps = batch * steps / (total_ms * 1e-3)
         e2e_qps = batch * steps / (e2e_ms * 1e-3)
-        algo = similarity.choose_algo(shard, q_dev, args.k)
+        algo = similarity.choose_algo(shard, q_dev, args.k) if cur_algo[0] == "auto" else cur_algo[0]
         use_gemm = algo == "gemm"
         k_avg = statistics.mean(kern_ms) if kern_ms else None
         roof = None
@@ -318,6 +331,7 @@ def run_ours(args):
     extra = None
     if not args.no_secondary and args.batch != 1:
         sec_steps = 50
+        cur_algo[0] = "auto"
         t2, k2, e2, c2 = measure(1, sec_steps, 5)
         if rank == 0:
             extra = {"query_batch_1": dict(describe(1, sec_steps, t2, k2, e2), steps=sec_steps, clocks=c2,
@@ -325,9 +339,9 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args), "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 storage, f32 accumulate", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": f"{args.dtype} storage, f32 accumulate", "data": "synthetic",
             "config": workload_config(args), "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
             "roofline": main_res["roofline"], "clocks": clocks,
         }

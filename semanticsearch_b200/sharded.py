@@ -61,10 +61,10 @@ class ShardedCorpus:
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
-    def search(self, queries: torch.Tensor, k: int):
+    def search(self, queries: torch.Tensor, k: int, algo: str = "auto"):
         """Global top-k for ``queries`` (replicated on every rank): ``(scores, indices)``."""
         scores, idx, keys = self._local_search(self.local_rows, queries, k, index_base=self.row_offset,
-                                               return_keys=True)
+                                               return_keys=True, algo=algo)
         world = self.world_size
         if world == 1:
             return scores, idx

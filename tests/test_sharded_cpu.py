@@ -36,7 +36,7 @@ def test_partition_documents_balances_cost():
         assert max(loads) / min(loads) < 1.01
 
 
-def _oracle_local_search(local_rows, queries, k, index_base=0, return_keys=True):
+def _oracle_local_search(local_rows, queries, k, index_base=0, return_keys=True, algo="auto"):
     s, i = ro.cosine_topk_ref(queries.numpy(), local_rows.numpy(), k)
     pad = k - s.shape[1]
     if pad:
