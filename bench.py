@@ -123,6 +123,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# DRAM traffic per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
+# `ncu --set full` captures committed under profiles/ — valid for exactly these single-GPU shapes.
+NCU_TRAFFIC = {
+    ("gemm", 10_000_000, 768, 4096): (42.633686e9 + 30.4e6, "profiles/r01_k2_v4_pair_ncu_summary.txt"),
+    ("stream", 10_000_000, 768, 1): (15.36e9, "profiles/r01_k1_v1_ncu_summary.txt (v2 capture: 15.36 GB read)"),
+    ("tcstream", 12_500_000, 384, 16): (9.601385e9 + 5.5e6, "profiles/r01_k7_cfg5_ncu_summary.txt"),
+}
+
+
+def ncu_traffic(algo, rows_local, dim, batch):
+    hit = NCU_TRAFFIC.get((algo, rows_local, dim, batch))
+    return (hit[0], hit[1]) if hit else (None, None)
+
+
 def metric_name(args):
     if (args.rows, args.dim, args.k, args.dtype) == (10_000_000, 768, 10, "bf16"):
         return METRIC
@@ -304,7 +318,8 @@ def run_ours(args):
             flops = 2.0 * batch * (hi - lo) * args.dim
             achieved = flops / (k_avg * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                    "frac_of_sustained_peak": achieved / tf_sustained if tf_sustained else None, "traffic": None,
+                    "frac_of_sustained_peak": achieved / tf_sustained if tf_sustained else None,
+                    "traffic": ncu_traffic(algo, hi - lo, args.dim, batch)[0], "traffic_source": ncu_traffic(algo, hi - lo, args.dim, batch)[1],
                     "kernel": "cosine_topk_gemm_kernel (tcgen05)", "kernel_ms": k_avg,
                     "kernel_share_of_step": k_avg * len(kern_ms) / total_ms, "peak_source": peak_src,
                     "algorithmic_flops_per_launch": flops}
@@ -315,7 +330,7 @@ def run_ours(args):
             alg_bytes = (hi - lo) * args.dim * 2 * groups + batch * args.dim * 2 + batch * args.k * 8
             achieved = alg_bytes / (k_avg * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None,
+                    "traffic": ncu_traffic(algo, hi - lo, args.dim, batch)[0], "traffic_source": ncu_traffic(algo, hi - lo, args.dim, batch)[1],
                     "kernel": "cosine_topk_tcstream_kernel (tcgen05)" if algo == "tcstream" else "cosine_topk_stream_kernel",
                     "kernel_ms": k_avg,
                     "kernel_share_of_step": k_avg * len(kern_ms) / total_ms, "peak_source": peak_src,

@@ -85,3 +85,37 @@ def test_gemm_large_batch_properties():
     rs, ri = torch.topk(ref, k, dim=1)
     assert torch.allclose(rs, s, atol=2e-5)
     assert (ri == i).float().mean().item() > 0.995
+
+
+def test_full_size_config4_properties():
+    """BASELINE config 4 at full size (10 M x 768 bf16, 4096 queries, top-10) through size-independent
+    properties: planted winners come first, lists are sorted and duplicate-free, the three kernels agree
+    on a query subset, and re-scoring the returned rows in fp32 reproduces the returned scores."""
+    from semanticsearch_b200 import similarity
+    free, _total = torch.cuda.mem_get_info()
+    if free < 24 * (1 << 30):
+        pytest.skip("needs ~20 GB of free HBM")
+    g = torch.Generator(device="cuda").manual_seed(6)
+    n, d, b, k = 10_000_000, 768, 4096, 10
+    C = torch.empty((n, d), dtype=torch.bfloat16, device="cuda")
+    for a in range(0, n, 1 << 20):
+        e = min(n, a + (1 << 20))
+        C[a:e] = torch.randn((e - a, d), generator=g, device="cuda").to(torch.bfloat16)
+    Q = torch.randn((b, d), generator=g, device="cuda").to(torch.bfloat16)
+    plant = torch.unique(torch.randint(0, n, (256,), generator=g, device="cuda"))
+    C[plant] = Q[: plant.numel()] * 2.0
+    s, i = similarity.cosine_topk(C, Q, k)                       # K2 (CTA pairs)
+    assert similarity.choose_algo(C, Q, k) == "gemm"
+    assert torch.equal(i[: plant.numel(), 0], plant) and torch.all(s[: plant.numel(), 0] > 0.999)
+    assert torch.all(s[:, 1:] <= s[:, :-1])
+    assert all(len(set(row)) == k for row in i[:64].tolist())
+    # fp32 re-score of the returned rows
+    rows = C[i[:32].reshape(-1)].float().view(32, k, d)
+    qn = torch.nn.functional.normalize(Q[:32].float(), dim=1)
+    ref = torch.einsum("bkd,bd->bk", torch.nn.functional.normalize(rows, dim=2), qn)
+    assert torch.allclose(ref, s[:32], atol=2e-5)
+    # the streaming kernels return the same lists
+    s7, i7 = similarity.cosine_topk(C, Q[:48].contiguous(), k, algo="tcstream")
+    assert (i7 == i[:48]).float().mean().item() > 0.995 and torch.allclose(s7, s[:48], atol=2e-5)
+    s1, i1 = similarity.cosine_topk(C, Q[:1].contiguous(), k, algo="stream")
+    assert (i1 == i[:1]).float().mean().item() >= 0.9 and torch.allclose(s1, s[:1], atol=2e-5)
