@@ -1,2 +1,5 @@
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_r1.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-grep -c . gpurun_out/launches_bench_r1.csv
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_rank.py tests/test_gpu_tcstream.py -x -q 2>&1 | tail -5
+for i in 1 2; do
+SS_GEMM_NO_SHARE=1 timeout 300 python benchmarks/sweep_topk.py --batches 4096 --algos gemm --steps 8 2>&1 | tail -n 1
+timeout 300 python benchmarks/sweep_topk.py --batches 4096 --algos gemm --steps 8 2>&1 | tail -n 1
+done

@@ -17,6 +17,7 @@
 // so that all query blocks of one chunk run concurrently and share corpus tiles through L2; each
 // unit writes k packed keys per query and ss_topk_merge folds the chunks.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -58,6 +59,7 @@ struct GemmParams {
   const float* inv_c;  // padded to a multiple of G_BN entries, NaN past n_rows (never selected)
   const float* inv_q;
   uint64_t* partial;  // [n_chunks * 2][n_queries][k]: one list per (chunk, column half)
+  uint32_t* gthr;     // [n_queries] best published k-th score per query (order-preserving bits), zeroed before launch
 };
 
 // Per-thread top-k list in shared memory, entry j of epilogue thread e at list[j * 128 + e]
@@ -230,7 +232,16 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         e.ix = -1;
         my_list[j * G_EPI_THREADS] = e;
       }
+      // Seed the threshold with the best k-th score an EARLIER unit of this query has published: whoever
+      // holds k rows scoring >= v proves that rows scoring < v cannot reach the global top-k, so the
+      // warm-up inserts of the first wave of (chunk, half) lists are not repeated by the later waves.
+      // One step below v: equal scores still compete on the row index.
       float thr = -INFINITY;
+      if (p.gthr != nullptr && query < p.n_queries) {
+        const uint32_t g = *reinterpret_cast<volatile uint32_t*>(p.gthr + query);
+        if (g > 1u) thr = ordered_to_float(g - 1u);
+      }
+      const float thr_floor = thr;
       for (long long t = t0; t < t1; ++t) {
         const float* inv_tile = sinv + acc * G_BN + half * G_EPI_COLS;
         mbar_wait(&inv_full[acc], acc_ph);
@@ -260,7 +271,7 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float sc = x[j] * inv_q;
-                if (sc > thr) thr = epi_list_insert(my_list, p.k, sc, col_base + c0 + j);
+                if (sc > thr) thr = fmaxf(thr_floor, epi_list_insert(my_list, p.k, sc, col_base + c0 + j));
               }
             }
           }
@@ -282,7 +293,7 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float sc = x[j] * inv_q;
-                if (sc > thr) thr = epi_list_insert(my_list, p.k, sc, col_base + c0 + 32 + j);
+                if (sc > thr) thr = fmaxf(thr_floor, epi_list_insert(my_list, p.k, sc, col_base + c0 + 32 + j));
               }
             }
           }
@@ -299,6 +310,8 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
       }
       if (query < p.n_queries) {
+        const float kth = my_list[(p.k - 1) * G_EPI_THREADS].v;  // -inf unless this list holds k rows
+        if (p.gthr != nullptr && kth > thr_floor) atomicMax(p.gthr + query, float_to_ordered(kth));
         uint64_t* out = p.partial + ((static_cast<size_t>(chunk) * 2 + half) * p.n_queries + query) * p.k;
         for (int j = 0; j < p.k; ++j) {
           const ScoreIdx e = my_list[j * G_EPI_THREADS];
@@ -393,7 +406,7 @@ extern "C" size_t ss_cosine_topk_gemm_workspace_bytes(int64_t n_rows, int dim, i
   if (n_rows <= 0 || n_queries <= 0 || k <= 0) return 0;
   const GemmPlan g = make_gemm_plan(n_rows, n_queries);
   return align_up(static_cast<size_t>(n_rows), G_BN) * 4 + align_up(static_cast<size_t>(n_queries) * 4, 256) +
-         align_up(static_cast<size_t>(g.n_chunks) * 2 * n_queries * k * 8, 256) + 256;
+         align_up(static_cast<size_t>(g.n_chunks) * 2 * n_queries * k * 8, 256) + align_up(static_cast<size_t>(n_queries) * 4, 256) + 256;
 }
 
 extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, int dtype, const void* queries, int n_queries,
@@ -418,6 +431,12 @@ extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, 
   float* inv_q = reinterpret_cast<float*>(ws);
   ws += align_up(static_cast<size_t>(n_queries) * 4, 256);
   uint64_t* partial = reinterpret_cast<uint64_t*>(ws);
+  {
+    const GemmPlan g0 = make_gemm_plan(n_rows, n_queries);
+    ws += align_up(static_cast<size_t>(g0.n_chunks) * 2 * n_queries * k * 8, 256);
+  }
+  uint32_t* gthr = reinterpret_cast<uint32_t*>(ws);
+  SS_CUDA_CHECK(cudaMemsetAsync(gthr, 0, static_cast<size_t>(n_queries) * 4, st));
 
   cudaError_t e;
   if (dtype == SS_BF16) {
@@ -449,6 +468,7 @@ extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, 
   p.inv_c = inv_c;
   p.inv_q = inv_q;
   p.partial = partial;
+  p.gthr = getenv("SS_GEMM_NO_SHARE") ? nullptr : gthr;
   const uint32_t idesc = make_idesc(dtype == SS_BF16 ? 1 : 0, G_BM * cg, G_BN);
   const size_t per_stage = cg == 2 ? GemmCfg<2>::kStageBytes : GemmCfg<1>::kStageBytes;
   const size_t fixed = 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4 + static_cast<size_t>(k) * G_EPI_THREADS * sizeof(ScoreIdx);
