@@ -1,2 +1,2 @@
-python benchmarks/sanitize_small.py > gpurun_out/san_plain.log 2>&1 && timeout 800 compute-sanitizer --tool memcheck --print-limit 20 python benchmarks/sanitize_small.py > gpurun_out/san_memcheck.log 2>&1
-tail -n 3 gpurun_out/san_plain.log; tail -n 15 gpurun_out/san_memcheck.log
+timeout 900 python -m pytest tests/test_gpu_fuzz.py tests/test_gpu_rank.py tests/test_gpu_ranker.py -x -q 2>&1 | tail -12
+python benchmarks/bench_configs.py --config 1 --steps 20 | tail -n 1

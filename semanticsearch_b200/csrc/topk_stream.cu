@@ -469,7 +469,12 @@ static bool make_config(const void* corpus, long long n_rows, int dim, int dtype
       cfg->tile_bytes = tile_bytes;
       cfg->n_tiles = (n_rows + tile_rows - 1) / tile_rows;
       cfg->grid_y = (n_queries + bt - 1) / bt;
-      cfg->grid_x = static_cast<int>(std::max<long long>(1, std::min<long long>(sms, cfg->n_tiles)));
+      // Several query groups (grid.y) share the SMs: with a small corpus a full-width grid per group
+      // only multiplies prologue / epilogue / merge work, so aim at ~2 CTAs per SM in total.
+      long long gx = std::min<long long>(sms, cfg->n_tiles);
+      if (cfg->grid_y > 1 && cfg->n_tiles < 8LL * sms)
+        gx = std::min<long long>(gx, std::max<long long>(1, (2LL * sms + cfg->grid_y - 1) / cfg->grid_y));
+      cfg->grid_x = static_cast<int>(std::max<long long>(1, gx));
       cfg->threads = kStreamThreads;
       cfg->smem = fixed + static_cast<size_t>(stages) * tile_bytes;
       return true;
