@@ -24,6 +24,28 @@ sys.path.insert(0, ROOT)
 from semanticsearch_b200 import ragged, similarity  # noqa: E402
 
 
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+
+
+def my_documents(sizes, power):
+    """Static LPT partition of the documents over the ranks (no cross-GPU traffic)."""
+    if WORLD == 1:
+        return np.asarray(sizes)
+    from semanticsearch_b200.sharded import partition_documents
+    part = partition_documents(sizes, WORLD, power=power)[RANK]
+    return np.asarray(sizes)[part]
+
+
+def max_over_ranks(ms):
+    if WORLD == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def hbm_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -82,12 +104,12 @@ def config1(args):
 def config2(args):
     rng = np.random.default_rng(3)
     D = args.docs or 10000
-    sizes = rng.integers(16, 513, size=D)
-    E = topic_rows(sizes, 768, 4, "cuda")
+    sizes = my_documents(rng.integers(16, 513, size=D), power=2)
+    E = topic_rows(sizes, 768, 4 + RANK, "cuda")
     plan = ragged.make_plan(sizes, "cuda")
     S = torch.empty(plan.total_s, dtype=torch.float32, device="cuda")
-    ms_sim = cuda_time(lambda: ragged.segmented_simmatrix(E, plan, out=S), args.steps)
-    ms_grp = cuda_time(lambda: ragged.group_threshold_pass(S, plan), max(1, args.steps // 2), warmup=1)
+    ms_sim = max_over_ranks(cuda_time(lambda: ragged.segmented_simmatrix(E, plan, out=S), args.steps))
+    ms_grp = max_over_ranks(cuda_time(lambda: ragged.group_threshold_pass(S, plan), max(1, args.steps // 2), warmup=1))
     peak, src = hbm_peak()
     alg = 4 * 768 * plan.total_rows + 4 * plan.total_s
     # K4 algorithmic traffic: read S, write sim_sharp, write the neighbour lists (33 x (int32 + fp32) per row) + centrality
@@ -99,7 +121,7 @@ def config2(args):
         pass
     # CPU: the reference's arithmetic for the same pass, on a sample of documents
     from oracle import grouping_oracle as go, simmatrix_oracle as so
-    sample = list(range(0, D, max(1, D // 40)))[:40]
+    sample = list(range(0, len(sizes), max(1, len(sizes) // 40)))[:40]
     Eh = [E[plan.offsets[d]:plan.offsets[d + 1]].cpu().numpy() for d in sample]
     t0 = time.perf_counter()
     for e in Eh:
@@ -127,9 +149,9 @@ def config2(args):
 
 def config3(args):
     rng = np.random.default_rng(5)
-    D = args.docs or 50000
-    sizes = rng.integers(16, 513, size=D)
-    E = topic_rows(sizes, 384, 5, "cuda")
+    D = (args.docs or 50000) * WORLD  # weak scaling: 50k documents per GPU
+    sizes = my_documents(rng.integers(16, 513, size=D), power=1)
+    E = topic_rows(sizes, 384, 5 + RANK, "cuda")
     plan = ragged.make_plan(sizes, "cuda")
     adj_holder = {}
 
@@ -137,12 +159,12 @@ def config3(args):
         adj = ragged.adjacent_cosine(E)
         adj_holder["out"] = ragged.segmented_percentile(adj, plan, 95.0, want_stats=False)
 
-    ms_adj = cuda_time(lambda: ragged.adjacent_cosine(E), args.steps)
-    ms_all = cuda_time(step, args.steps)
+    ms_adj = max_over_ranks(cuda_time(lambda: ragged.adjacent_cosine(E), args.steps))
+    ms_all = max_over_ranks(cuda_time(step, args.steps))
     peak, src = hbm_peak()
     alg = 4 * 384 * plan.total_rows + 4 * plan.total_rows + 8 * D
     from oracle import splitter_oracle as spo
-    sample = list(range(0, D, max(1, D // 200)))[:200]
+    sample = list(range(0, len(sizes), max(1, len(sizes) // 200)))[:200]
     Eh = [E[plan.offsets[d]:plan.offsets[d + 1]].cpu().numpy() for d in sample]
     t0 = time.perf_counter()
     for e in Eh:
@@ -183,9 +205,22 @@ def main():
     ap.add_argument("--docs", type=int, default=0)
     ap.add_argument("--rows", type=int, default=0)
     args = ap.parse_args()
+    if WORLD > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+        if args.config not in (2, 3):
+            raise SystemExit("multi-GPU runs of this script cover the ragged configs 2 and 3 (bench.py covers 4 and 5)")
     res = {1: config1, 2: config2, 3: config3, 5: config5}[args.config](args)
     res["data"] = "synthetic"
-    print(json.dumps(res))
+    res["n_gpus"] = WORLD
+    if WORLD > 1:
+        res["partition"] = "static LPT over documents, no data-path collective; time = max over ranks"
+        dist.barrier()
+    if RANK == 0:
+        print(json.dumps(res))
+    if WORLD > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -57,6 +57,7 @@ struct GemmParams {
   long long n_units;
   int stages;
   const float* inv_c;  // padded to a multiple of G_BN entries, NaN past n_rows (never selected)
+  const float* inv_gmax;  // [n_fill / 32] largest 1/|c| of each 32-row group (NaN rows ignored)
   const float* inv_q;
   uint64_t* partial;  // [n_chunks * 2][n_queries][k]: one list per (chunk, column half)
   uint32_t* gthr;     // [n_queries] best published k-th score per query (order-preserving bits), zeroed before launch
@@ -84,6 +85,29 @@ __device__ __noinline__ float epi_list_insert(ScoreIdx* list, int k, float sc, i
   return list[(k - 1) * G_EPI_THREADS].v;
 }
 
+// One 32-column group of one query row.  Cheap bound first: with a non-negative threshold no column can
+// beat it unless max(raw dot) * max(1/|c| of the group) * 1/|q| does, which needs no per-column multiply;
+// the exact scores (raw * 1/|c| * 1/|q|) are formed only for the rare group that passes.
+__device__ __forceinline__ void epi_group(const uint32_t (&r)[32], const float* inv_grp, float gmax, float inv_q, float& thr,
+                                          float thr_floor, ScoreIdx* my_list, int k, int col0) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    m = fmaxf(fmaxf(fmaxf(m, __uint_as_float(r[j])), fmaxf(__uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]))), __uint_as_float(r[j + 3]));
+  if (thr < 0.f || fmaxf(m, 0.f) * gmax * inv_q > thr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 iv = *reinterpret_cast<const float4*>(inv_grp + j);
+      const float ivs[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float sc = (__uint_as_float(r[j + e]) * ivs[e]) * inv_q;
+        if (sc > thr) thr = fmaxf(thr_floor, epi_list_insert(my_list, k, sc, col0 + j + e));
+      }
+    }
+  }
+}
+
 template <int CG>
 __global__ void __launch_bounds__(G_THREADS, 1)
 cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
@@ -98,7 +122,8 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
   unsigned char* tiles = smem;
   float* sinv = reinterpret_cast<float*>(tiles + static_cast<size_t>(G_STAGES) * G_STAGE_BYTES);  // [2][G_BN] corpus inverse norms
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sinv + 2 * G_BN);
+  float* sgmax = sinv + 2 * G_BN;                                                                  // [2][G_BN / 32] their 32-row group maxima
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sgmax + 2 * (G_BN / 32));
   uint64_t* empty_bar = full_bar + G_MAX_STAGES;
   uint64_t* tmem_full = empty_bar + G_MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -146,8 +171,9 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (long long t = t0; t < t1; ++t) {
           // this tile's 256 corpus inverse norms (1 KB) ride the TMA engine too
           mbar_wait(&inv_empty[ia], ia_ph ^ 1u);
-          mbar_arrive_expect_tx(&inv_full[ia], G_BN * 4);
+          mbar_arrive_expect_tx(&inv_full[ia], G_BN * 4 + (G_BN / 32) * 4);
           bulk_copy_g2s(sinv + ia * G_BN, p.inv_c + t * G_BN, G_BN * 4, &inv_full[ia]);
+          bulk_copy_g2s(sgmax + ia * (G_BN / 32), p.inv_gmax + t * (G_BN / 32), (G_BN / 32) * 4, &inv_full[ia]);
           if (++ia == 2) {
             ia = 0;
             ia_ph ^= 1u;
@@ -244,6 +270,7 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const float thr_floor = thr;
       for (long long t = t0; t < t1; ++t) {
         const float* inv_tile = sinv + acc * G_BN + half * G_EPI_COLS;
+        const float* gmax_tile = sgmax + acc * (G_BN / 32) + half * (G_EPI_COLS / 32);
         mbar_wait(&inv_full[acc], acc_ph);
         mbar_wait(&tmem_full[acc], acc_ph);
         tc_fence_after();
@@ -255,48 +282,10 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int c0 = 0; c0 < G_EPI_COLS; c0 += 64) {
           tmem_ld_wait();                                   // ra = columns c0 .. c0+31
           tmem_ld32(taddr + static_cast<uint32_t>(c0 + 32), rb);  // in flight while ra is processed
-          {
-            float m = -INFINITY;
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 iv = *reinterpret_cast<const float4*>(inv_tile + c0 + j);
-              x[j] = __uint_as_float(ra[j]) * iv.x;
-              x[j + 1] = __uint_as_float(ra[j + 1]) * iv.y;
-              x[j + 2] = __uint_as_float(ra[j + 2]) * iv.z;
-              x[j + 3] = __uint_as_float(ra[j + 3]) * iv.w;
-              m = fmaxf(fmaxf(fmaxf(m, x[j]), fmaxf(x[j + 1], x[j + 2])), x[j + 3]);
-            }
-            if (m * inv_q > thr) {  // rare once the list has warmed up
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float sc = x[j] * inv_q;
-                if (sc > thr) thr = fmaxf(thr_floor, epi_list_insert(my_list, p.k, sc, col_base + c0 + j));
-              }
-            }
-          }
+          epi_group(ra, inv_tile + c0, gmax_tile[c0 >> 5], inv_q, thr, thr_floor, my_list, p.k, col_base + c0);
           tmem_ld_wait();                                   // rb = columns c0+32 .. c0+63
           if (c0 + 64 < G_EPI_COLS) tmem_ld32(taddr + static_cast<uint32_t>(c0 + 64), ra);
-          {
-            float m = -INFINITY;
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 iv = *reinterpret_cast<const float4*>(inv_tile + c0 + 32 + j);
-              x[j] = __uint_as_float(rb[j]) * iv.x;
-              x[j + 1] = __uint_as_float(rb[j + 1]) * iv.y;
-              x[j + 2] = __uint_as_float(rb[j + 2]) * iv.z;
-              x[j + 3] = __uint_as_float(rb[j + 3]) * iv.w;
-              m = fmaxf(fmaxf(fmaxf(m, x[j]), fmaxf(x[j + 1], x[j + 2])), x[j + 3]);
-            }
-            if (m * inv_q > thr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float sc = x[j] * inv_q;
-                if (sc > thr) thr = fmaxf(thr_floor, epi_list_insert(my_list, p.k, sc, col_base + c0 + 32 + j));
-              }
-            }
-          }
+          epi_group(rb, inv_tile + c0 + 32, gmax_tile[(c0 >> 5) + 1], inv_q, thr, thr_floor, my_list, p.k, col_base + c0 + 32);
         }
         tc_fence_before();
         __syncwarp();
@@ -366,6 +355,20 @@ __global__ void __launch_bounds__(256) row_inv_norms_vec_kernel(const T* __restr
   }
 }
 
+// largest finite inverse norm of every 32-row group (feeds the epilogue's multiply-free bound)
+__global__ void __launch_bounds__(256) inv_group_max_kernel(const float* __restrict__ inv, long long n_groups, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long g = warp; g < n_groups; g += nwarps) {
+    float v = inv[g * 32 + lane];
+    v = (v == v) ? v : 0.f;  // NaN marks rows past the end
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) out[g] = v;
+  }
+}
+
 template <typename T>
 static cudaError_t launch_inv_norms_vec(const void* rows, long long n_rows, int dim, float zero_value, float* out, long long n_fill,
                                         cudaStream_t st) {
@@ -382,7 +385,39 @@ struct GemmPlan {
   int n_chunks;
 };
 
-static int gemm_cta_group(int n_queries) { return (n_queries > G_BM && sm_count() % 2 == 0) ? 2 : 1; }
+// CTA pairs need cluster launches of 2 CTAs with ~212 KB of shared memory each to be schedulable on this
+// device (they are on a full B200; MIG slices or an odd SM count fall back to single-CTA tiles).
+static bool gemm_pairs_supported() {
+  static int cached[64];  // 0 = unknown, 1 = yes, 2 = no
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (cached[dev] == 0) {
+    bool ok = sm_count() % 2 == 0;
+    if (ok) {
+      const size_t smem = smem_optin() - 1024;
+      ok = cudaFuncSetAttribute(cosine_topk_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
+      if (ok) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(2);
+        lc.blockDim = dim3(G_THREADS);
+        lc.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        int n_clusters = 0;
+        ok = cudaOccupancyMaxActiveClusters(&n_clusters, cosine_topk_gemm_kernel<2>, &lc) == cudaSuccess && n_clusters >= 1;
+      }
+      cudaGetLastError();  // a failed probe must not poison later launches
+    }
+    cached[dev] = ok ? 1 : 2;
+  }
+  return cached[dev] == 1;
+}
+static int gemm_cta_group(int n_queries) { return (n_queries > G_BM && gemm_pairs_supported()) ? 2 : 1; }
 
 static GemmPlan make_gemm_plan(long long n_rows, int n_queries) {
   GemmPlan g;
@@ -405,7 +440,8 @@ extern "C" size_t ss_cosine_topk_gemm_workspace_bytes(int64_t n_rows, int dim, i
   (void)dim;
   if (n_rows <= 0 || n_queries <= 0 || k <= 0) return 0;
   const GemmPlan g = make_gemm_plan(n_rows, n_queries);
-  return align_up(static_cast<size_t>(n_rows), G_BN) * 4 + align_up(static_cast<size_t>(n_queries) * 4, 256) +
+  return align_up(static_cast<size_t>(n_rows), G_BN) * 4 + align_up(align_up(static_cast<size_t>(n_rows), G_BN) / 32 * 4, 256) +
+         align_up(static_cast<size_t>(n_queries) * 4, 256) +
          align_up(static_cast<size_t>(g.n_chunks) * 2 * n_queries * k * 8, 256) + align_up(static_cast<size_t>(n_queries) * 4, 256) + 256;
 }
 
@@ -428,6 +464,8 @@ extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, 
   float* inv_c = reinterpret_cast<float*>(ws);
   const long long n_fill = static_cast<long long>(align_up(static_cast<size_t>(n_rows), G_BN));
   ws += static_cast<size_t>(n_fill) * 4;
+  float* inv_gmax = reinterpret_cast<float*>(ws);
+  ws += align_up(static_cast<size_t>(n_fill) / 32 * 4, 256);
   float* inv_q = reinterpret_cast<float*>(ws);
   ws += align_up(static_cast<size_t>(n_queries) * 4, 256);
   uint64_t* partial = reinterpret_cast<uint64_t*>(ws);
@@ -445,6 +483,12 @@ extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, 
   } else {
     e = launch_inv_norms_vec<__half>(corpus, n_rows, dim, 1.0f, inv_c, n_fill, st);
     if (e == cudaSuccess) e = launch_inv_norms_vec<__half>(queries, n_queries, dim, 1.0f, inv_q, 0, st);
+  }
+  if (e == cudaSuccess) {
+    const long long n_groups = n_fill / 32;
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((n_groups + 7) / 8, static_cast<long long>(sm_count()) * 8)));
+    inv_group_max_kernel<<<blocks, 256, 0, st>>>(inv_c, n_groups, inv_gmax);
+    e = cudaGetLastError();
   }
   if (e != cudaSuccess) return cuda_fail(e, "row_inv_norms_vec launch");
 
@@ -466,12 +510,13 @@ extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, 
   p.n_chunks = g.n_chunks;
   p.n_units = static_cast<long long>(g.n_chunks) * g.n_qb;
   p.inv_c = inv_c;
+  p.inv_gmax = inv_gmax;
   p.inv_q = inv_q;
   p.partial = partial;
   p.gthr = getenv("SS_GEMM_NO_SHARE") ? nullptr : gthr;
   const uint32_t idesc = make_idesc(dtype == SS_BF16 ? 1 : 0, G_BM * cg, G_BN);
   const size_t per_stage = cg == 2 ? GemmCfg<2>::kStageBytes : GemmCfg<1>::kStageBytes;
-  const size_t fixed = 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4 + static_cast<size_t>(k) * G_EPI_THREADS * sizeof(ScoreIdx);
+  const size_t fixed = 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4 + 2 * (G_BN / 32) * 4 + static_cast<size_t>(k) * G_EPI_THREADS * sizeof(ScoreIdx);
   p.stages = static_cast<int>(std::min<size_t>(cg == 2 ? GemmCfg<2>::kMaxStages : GemmCfg<1>::kMaxStages, (smem_optin() - fixed) / per_stage));
   if (p.stages < 2) return fail(SS_ERR_UNSUPPORTED, "ss_cosine_topk_gemm: not enough shared memory");
   const size_t smem = fixed + static_cast<size_t>(p.stages) * per_stage;

@@ -15,6 +15,7 @@ from . import _lib
 from .similarity import _dtype_code, _require_cuda, _stream_ptr
 
 KNN_WIDTH = 33
+TC_MAX_DIM = 768  # largest embedding width the 3xTF32 similarity kernel is dispatched for
 
 
 @dataclass
@@ -94,11 +95,12 @@ def segmented_simmatrix(E: torch.Tensor, plan: RaggedPlan, out: Optional[torch.T
         raise ValueError(f"E has {E.shape[0]} rows, plan expects {plan.total_rows}")
     if algo not in ("auto", "tc", "ffma"):
         raise ValueError("algo must be 'auto', 'tc' or 'ffma'")
-    # The tensor core truncates when it accumulates, a bias that grows with dim (measured 5.6e-6 at
-    # dim = 768): past 1024 dimensions the CUDA-core fp32 kernel keeps the 1e-5 parity bound.
-    tc_ok = E.shape[1] % 4 == 0 and E.shape[1] <= 1024 and E.data_ptr() % 16 == 0 and plan.total_rows > 0
+    # The tensor core truncates when it accumulates, a bias that grows with dim and with |S| (measured
+    # 5.6e-6 at dim = 768 on the diagonal, 2.9e-6 at 384): past 768 dimensions the CUDA-core fp32 kernel
+    # keeps a safe margin to the 1e-5 parity bound.
+    tc_ok = E.shape[1] % 4 == 0 and E.shape[1] <= TC_MAX_DIM and E.data_ptr() % 16 == 0 and plan.total_rows > 0
     if algo == "tc" and not tc_ok:
-        raise ValueError("the tensor-core similarity kernel needs dim % 4 == 0, dim <= 1024 and 16-byte aligned rows")
+        raise ValueError(f"the tensor-core similarity kernel needs dim % 4 == 0, dim <= {TC_MAX_DIM} and 16-byte aligned rows")
     use_tc = tc_ok if algo == "auto" else algo == "tc"
     lib = _lib.load()
     with torch.cuda.device(dev):

@@ -56,6 +56,7 @@ def workspace(dev: torch.device, nbytes: int, tag: str = "default") -> torch.Ten
 TC_MIN_BATCH = 2
 GEMM_MIN_BATCH = 96
 _ALGOS = ("auto", "stream", "gemm", "tcstream")
+_TCSTREAM_WS_BUDGET = 1 << 30  # bytes of partial top-k lists per K7 call
 
 
 def _lowp_eligible(corpus: torch.Tensor, queries: torch.Tensor) -> bool:
@@ -122,12 +123,17 @@ def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_ba
                 ws.numel(), keys_ptr, scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
             _lib.check(st, "ss_cosine_topk_gemm")
         elif algo == "tcstream":
-            need = lib.ss_cosine_topk_tcstream_workspace_bytes(n, d, b, k)
-            ws = workspace(dev, need)
-            st = lib.ss_cosine_topk_tcstream(
-                corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, k, int(index_base), ws.data_ptr(),
-                ws.numel(), keys_ptr, scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
-            _lib.check(st, "ss_cosine_topk_tcstream")
+            # per-CTA partial lists cost ~148 * k * 8 bytes per query: very large batches go through in slices
+            step = max(64, min(b, (_TCSTREAM_WS_BUDGET // (160 * k * 8)) // 64 * 64))
+            for q0 in range(0, b, step):
+                q1 = min(b, q0 + step)
+                need = lib.ss_cosine_topk_tcstream_workspace_bytes(n, d, q1 - q0, k)
+                ws = workspace(dev, need)
+                st = lib.ss_cosine_topk_tcstream(
+                    corpus.data_ptr(), n, d, _dtype_code(corpus), queries[q0:q1].data_ptr(), q1 - q0, k, int(index_base),
+                    ws.data_ptr(), ws.numel(), keys[q0:q1].data_ptr() if keys is not None else None,
+                    scores[q0:q1].data_ptr(), idx[q0:q1].data_ptr(), _stream_ptr(dev))
+                _lib.check(st, "ss_cosine_topk_tcstream")
         else:
             need = lib.ss_cosine_topk_stream_workspace_bytes(n, d, _dtype_code(corpus), b, k)
             ws = workspace(dev, need)
