@@ -316,10 +316,29 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
 
   // ---- 1. mean / std over all n^2 entries (fp64 accumulation, rounded to fp32 like numpy's result) ----
   double s1 = 0.0, s2 = 0.0;
-  for (long long i = tid; i < nn; i += kGrpThreads) {
-    const double v = static_cast<double>(S[i]);
-    s1 += v;
-    s2 += v * v;
+  {
+    // eight independent loads per thread and iteration: the pass is a pure stream over S and would
+    // otherwise be bound by load latency (one 4-byte load in flight per thread)
+    double t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
+    long long i0 = 0;
+    for (; i0 + 8 * kGrpThreads <= nn; i0 += 8 * kGrpThreads) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = S[i0 + q * kGrpThreads + tid];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double d = static_cast<double>(v[q]);
+        t1[q & 1] += d;
+        t2[q & 1] += d * d;
+      }
+    }
+    for (long long i = i0 + tid; i < nn; i += kGrpThreads) {
+      const double d = static_cast<double>(S[i]);
+      t1[0] += d;
+      t2[0] += d * d;
+    }
+    s1 = t1[0] + t1[1];
+    s2 = t2[0] + t2[1];
   }
   for (int i = tid; i < kRadixBins; i += kGrpThreads) hist[0][i] = 0u;  // pass-0 histogram (shared by the three targets)
   s1 = block_sum(s1, red);
@@ -446,15 +465,15 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
       if (tid < kNumQ) t_fill[tid] = 0u;
       __syncthreads();
       unsigned int a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
-      for (long long i0 = 0; i0 < nn; i0 += 4 * kGrpThreads) {
-        unsigned int bb[4];
+      for (long long i0 = 0; i0 < nn; i0 += 8 * kGrpThreads) {
+        unsigned int bb[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
           const long long i = i0 + q * kGrpThreads + tid;
           bb[q] = i < nn ? __float_as_uint(sharp[i]) : 0u;
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
           const unsigned int b = bb[q];
           if (b == 0u) continue;  // diagonal / underflowed zeros are not "positive values"
           const unsigned int bin = lin_bin(__uint_as_float(b));
