@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="multi-GPU exchange of the per-GPU top-k keys: NCCL all-gather + merge, or the fused NVLink peer-memory push + merge")
     ap.add_argument("--graphs", default="on", choices=["on", "off"],
                     help="replay the search (local kernels + all-gather + merge) as one CUDA graph in the timed loops")
     ap.add_argument("--algo", default="auto", choices=["auto", "stream", "tcstream", "gemm"],
@@ -150,7 +152,9 @@ def workload_config(args):
     return {"workload": f"{tag}: brute-force top-{args.k} cosine, {args.rows}x{args.dim} {args.dtype} corpus (not pre-normalised), "
                         f"query batch {args.batch}",
             "rows": args.rows, "dim": args.dim, "k": args.k, "query_batch": args.batch,
-            "sharding": f"corpus rows split {args.gpus}-way, queries replicated, all-gather of top-k keys",
+            "sharding": f"corpus rows split {args.gpus}-way, queries replicated, "
+                        + ("top-k keys pushed over NVLink peer memory and merged" if getattr(args, "exchange", "nccl") == "peer" and args.gpus > 1
+                           else "all-gather of top-k keys"),
             "l2": "inputs exceed L2 (per-GPU shard >= 1.9 GB vs 126 MB L2); no flush needed"}
 
 
@@ -242,7 +246,11 @@ def run_ours(args):
     lo, hi = shard_bounds(args.rows, world, rank)
     tdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     shard = make_shard(hi - lo, args.dim, 6 + rank, dev, tdtype)
-    corpus = ShardedCorpus(shard, lo)
+    peer = None
+    if world > 1 and args.exchange == "peer":
+        from semanticsearch_b200.sharded import PeerExchange
+        peer = PeerExchange(dev, max(args.batch, 1), args.k)
+    corpus = ShardedCorpus(shard, lo, peer_exchange=peer)
     q_host = q_dev = out_s_host = out_i_host = None
     cur_algo = [args.algo]
     lib = _lib.load()
@@ -394,6 +402,8 @@ def run_ours(args):
             line["cpu_baseline"], _ = cpu_reference_qps(args)
         print(json.dumps(line))
     if world > 1:
+        if peer is not None:
+            peer.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -115,6 +115,25 @@ int ss_topk_merge(const uint64_t* keys_in, int n_lists, int n_queries, int k_in,
                   int64_t query_stride, int64_t list_stride, int k_out,
                   uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
 
+/* ---- K6p: top-k key exchange over NVLink peer memory, fused with the merge -----------------------
+ * One box, one process per GPU.  Every rank allocates an exchange buffer (ss_peer_alloc: cudaMalloc +
+ * CUDA IPC handle), the 64-byte handles travel through the host (e.g. torch.distributed
+ * all_gather_object), and every rank maps its peers' buffers (ss_peer_open).  ss_topk_peer_exchange_merge
+ * then replaces "NCCL all-gather of B x k keys + ss_topk_merge": a push kernel stores this rank's keys
+ * into slot [rank] of every rank's buffer through the peer mappings and raises a per-rank flag, a merge
+ * kernel (one CTA per query) waits on its own buffer's flags and merges the `world` lists.
+ * peer_bases_device: DEVICE array of `world` pointers (entry r = rank r's buffer as mapped in this
+ * process, entry `rank` = the local allocation).  seq: 1, 2, 3, ... identical on every rank for the same
+ * search.  All ranks must call in lock-step (the wait is bounded and traps after seconds). */
+size_t ss_peer_buffer_bytes(int world, int max_queries, int k);
+int ss_peer_alloc(size_t bytes, void** dev_ptr_out, unsigned char* handle_out64);
+int ss_peer_open(const unsigned char* handle64, void** dev_ptr_out);
+int ss_peer_close(void* dev_ptr);
+int ss_peer_free(void* dev_ptr);
+int ss_topk_peer_exchange_merge(const uint64_t* local_keys, int n_queries, int k, int rank, int world,
+                                void* const* peer_bases_device, int max_queries, uint32_t seq,
+                                uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
+
 /* Row inverse L2 norms, 1/sqrt(sum x^2) with zero rows -> zero_value (1.0 reproduces sklearn,
  * Tool/rank_chunks_optimized.py:216; 1e9 reproduces norms[norms==0]=1e-9 at
  * Method/semantic_common.py:158-160). */

@@ -39,6 +39,13 @@ _SIGNATURES = {
     "ss_rank_order": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "ss_topk_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
+    "ss_peer_buffer_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ss_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "ss_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "ss_peer_close": (c_int, [c_void_p]),
+    "ss_peer_free": (c_int, [c_void_p]),
+    "ss_topk_peer_exchange_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_uint32, c_void_p, c_void_p,
+                                            c_void_p, c_void_p]),
     "ss_segmented_plan_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int)]),
     "ss_segmented_simmatrix": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "ss_segmented_plan128_host": (c_int, [c_void_p, c_int, c_void_p, c_int64, POINTER(c_int64)]),

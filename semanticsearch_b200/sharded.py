@@ -42,14 +42,80 @@ def partition_documents(sizes, world_size: int, power: int = 1):
     return [sorted(p) for p in parts]
 
 
+class PeerExchange:
+    """Top-k key exchange over NVLink peer memory (CUDA IPC) fused with the merge — the latency-bound
+    replacement of "NCCL all-gather + merge" for the ranks of one box (csrc/peer_exchange.cu)."""
+
+    def __init__(self, device: torch.device, max_queries: int, k: int, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+
+        from . import _lib
+        self.lib = _lib.load()
+        self._check = _lib.check
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.max_queries, self.k = int(max_queries), int(k)
+        self.device = device
+        self.seq = 0
+        nbytes = self.lib.ss_peer_buffer_bytes(self.world, self.max_queries, self.k)
+        if nbytes == 0:
+            raise ValueError("unsupported world size / max_queries / k for the peer exchange")
+        with torch.cuda.device(device):
+            ptr = ctypes.c_void_p()
+            handle = (ctypes.c_ubyte * 64)()
+            self._check(self.lib.ss_peer_alloc(nbytes, ctypes.byref(ptr), handle), "ss_peer_alloc")
+            self.local_ptr = ptr.value
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self.peer_ptrs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.peer_ptrs.append(self.local_ptr)
+                    continue
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                out = ctypes.c_void_p()
+                self._check(self.lib.ss_peer_open(buf, ctypes.byref(out)), "ss_peer_open")
+                self.peer_ptrs.append(out.value)
+            self.bases = torch.tensor(self.peer_ptrs, dtype=torch.int64, device=device)
+        dist.barrier(group=group)  # every buffer is mapped everywhere before the first push
+
+    def exchange_merge(self, keys: torch.Tensor):
+        """``keys``: this rank's int64 ``[B, k]`` packed keys -> global ``(scores, indices)`` on every rank."""
+        b, k = keys.shape
+        if k != self.k or b > self.max_queries:
+            raise ValueError(f"exchange was sized for k={self.k}, <= {self.max_queries} queries")
+        self.seq += 1
+        dev = keys.device
+        with torch.cuda.device(dev):
+            scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+            idx = torch.empty((b, k), dtype=torch.int64, device=dev)
+            st = self.lib.ss_topk_peer_exchange_merge(keys.data_ptr(), b, k, self.rank, self.world, self.bases.data_ptr(),
+                                                      self.max_queries, self.seq, None, scores.data_ptr(), idx.data_ptr(),
+                                                      torch.cuda.current_stream(dev).cuda_stream)
+            self._check(st, "ss_topk_peer_exchange_merge")
+        return scores, idx
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody unmaps while a peer may still push
+        for r, p in enumerate(self.peer_ptrs):
+            if r != self.rank and p:
+                self.lib.ss_peer_close(p)
+        self.lib.ss_peer_free(self.local_ptr)
+        self.peer_ptrs = []
+
+
 class ShardedCorpus:
     """One rank's shard of a row-sharded corpus, resident in HBM."""
 
     def __init__(self, local_rows: torch.Tensor, row_offset: int, group: Optional[dist.ProcessGroup] = None,
-                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 peer_exchange: Optional["PeerExchange"] = None):
         self.local_rows = local_rows
         self.row_offset = int(row_offset)
         self.group = group
+        self.peer_exchange = peer_exchange
         if local_search is None or merge is None:
             from . import similarity
             local_search = local_search or similarity.cosine_topk
@@ -69,6 +135,8 @@ class ShardedCorpus:
         if world == 1:
             return scores, idx
         b, kk = keys.shape
+        if self.peer_exchange is not None and kk == self.peer_exchange.k and b <= self.peer_exchange.max_queries:
+            return self.peer_exchange.exchange_merge(keys.contiguous())
         gathered = torch.empty((world * b, kk), dtype=keys.dtype, device=keys.device)  # rank-major concatenation
         dist.all_gather_into_tensor(gathered, keys.contiguous(), group=self.group)
         scores, idx, _ = self._merge(gathered.view(world, b, kk), k)
