@@ -196,7 +196,11 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
     uint32_t ph = 0, acc_ph = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int4 e = __ldg(p.units + u);
-      const bool active = srow < 128 || e.y != e.z;  // diagonal tiles have no separate B rows
+      const int n_doc = __ldg(p.offsets + e.x + 1) - __ldg(p.offsets + e.x);
+      // diagonal tiles have no separate B rows; rows past the end of the document (the tile is padded with
+      // whatever follows in memory) feed only outputs that are never written, so they are not split either
+      const int blk = srow < 128 ? e.y : e.z;
+      const bool active = (srow < 128 || e.y != e.z) && (blk * S_BM + r < n_doc);
       float ssq0 = 0.f, ssq1 = 0.f;
       for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(&full_bar[s], ph);
