@@ -198,9 +198,47 @@ def config5(args):
                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": src, "algorithmic_bytes_per_launch": alg}}
 
 
+def config6(args):
+    """Not a BASELINE.json config: the per-query body of rank_and_filter (cosine, two rank lookups, RRF, fused order,
+    percentile thresholds) for a block of query groups in one launch (K8)."""
+    rng = np.random.default_rng(11)
+    G = args.docs or 2000
+    sizes = rng.integers(50, 1001, size=G)
+    rows = int(sizes.sum())
+    C = torch.randn((rows, 768), generator=torch.Generator(device="cuda").manual_seed(12), device="cuda")
+    Q = torch.randn((G, 768), generator=torch.Generator(device="cuda").manual_seed(13), device="cuda")
+    bm = torch.rand(rows, generator=torch.Generator(device="cuda").manual_seed(14), device="cuda")
+    off = np.zeros(G + 1, dtype=np.int32)
+    off[1:] = np.cumsum(sizes)
+    off_d = torch.from_numpy(off).cuda()
+    ms = cuda_time(lambda: similarity.segmented_rank_rrf(C, off_d, Q, bm, max_group_rows=int(sizes.max())), args.steps)
+    peak, src = hbm_peak()
+    alg = 4 * 768 * rows + 4 * rows + rows * (4 + 4 + 4 + 8 + 4)
+    from sklearn.metrics.pairwise import cosine_similarity
+    sample = list(range(0, G, max(1, G // 50)))[:50]
+    Ch = [C[off[g]:off[g + 1]].cpu().numpy() for g in sample]
+    Qh = [Q[g:g + 1].cpu().numpy() for g in sample]
+    Bh = [bm[off[g]:off[g + 1]].cpu().numpy().astype(np.float64) for g in sample]
+    t0 = time.perf_counter()
+    for c, q, b in zip(Ch, Qh, Bh):
+        cs = cosine_similarity(q, c)[0]
+        n = len(cs)
+        rc = np.empty(n); rc[np.argsort(-cs)] = np.arange(1, n + 1)
+        rb = np.empty(n); rb[np.argsort(-b)] = np.arange(1, n + 1)
+        rrf = 1.0 / (60 + rc) + 1.0 / (60 + rb)
+        np.argsort(-rrf); np.percentile(rrf, 80); np.percentile(rrf, 20)
+    cpu_s = (time.perf_counter() - t0) / len(sample)
+    return {"config": f"rank groups (8f-3): {G} query groups, n~U[50,1000] chunks x 768 fp32: cosine + ranks + RRF + order + P80/P20",
+            "metric": "groups/s", "value": G / (ms * 1e-3), "ms": ms, "rows": rows,
+            "roofline": {"bound": "hbm", "kernel": "segmented_rank_rrf_kernel", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": src, "algorithmic_bytes_per_launch": alg},
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "groups/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                             "sample": f"{len(sample)} groups: rank_chunks_optimized.py:215-250,518-519 without BM25 scoring"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True, choices=[1, 2, 3, 5])
+    ap.add_argument("--config", type=int, required=True, choices=[1, 2, 3, 5, 6])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--docs", type=int, default=0)
     ap.add_argument("--rows", type=int, default=0)
@@ -211,7 +249,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
         if args.config not in (2, 3):
             raise SystemExit("multi-GPU runs of this script cover the ragged configs 2 and 3 (bench.py covers 4 and 5)")
-    res = {1: config1, 2: config2, 3: config3, 5: config5}[args.config](args)
+    res = {1: config1, 2: config2, 3: config3, 5: config5, 6: config6}[args.config](args)
     res["data"] = "synthetic"
     res["n_gpus"] = WORLD
     if WORLD > 1:

@@ -80,6 +80,20 @@ size_t ss_rank_order_workspace_bytes(int n_queries, int64_t n);
 int ss_rank_order(const float* scores, int n_queries, int64_t n, void* workspace, size_t workspace_bytes,
                   int32_t* out_order, int32_t* out_rank1, void* stream);
 
+/* ---- K8: segmented ranking of query groups (cosine, ranks, reciprocal-rank fusion, percentiles) ----
+ * For every group g (chunk rows offsets[g]..offsets[g+1] of the fp32 matrix `chunks`, query g of `queries`), in
+ * one launch: out_cos = cosine_similarity(q, chunks)[0] (Tool/rank_chunks_optimized.py:215-216);
+ * out_rank_cos / out_rank_bm25 = the 1-based rank lookups of np.argsort(-scores) (:225-235; bm25_scores are
+ * computed by the caller, NULL skips the lexical term); out_rrf = 1/(k_rrf + rank_cos) + 1/(k_rrf + rank_bm25)
+ * in fp64 (:238-239); out_order = the group's local row indices by fused score, best first (:250);
+ * out_thr[g] = {np.percentile(rrf, upper), np.percentile(rrf, lower)} (:518-519).  Equal scores rank
+ * lower-row-first.  max_group_rows <= 8192. */
+int ss_segmented_rank_rrf(const float* chunks, int dim, const int32_t* offsets, int n_groups, int max_group_rows,
+                          const float* queries, const float* bm25_scores, double k_rrf,
+                          double upper_percentile, double lower_percentile,
+                          float* out_cos, int32_t* out_rank_cos, int32_t* out_rank_bm25, double* out_rrf,
+                          int32_t* out_order, double* out_thr, void* stream);
+
 /* ---- K2: tensor-core cosine + fused top-k, large query batches ---------------------------------
  * Same contract as ss_cosine_topk_stream for bf16/fp16 corpora and queries of the same dtype, k <= 16,
  * dim % 8 == 0: D = Q C^T on tcgen05 tensor cores (TMA-fed shared-memory operands, fp32

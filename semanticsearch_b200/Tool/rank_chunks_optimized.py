@@ -8,7 +8,9 @@ Same public names and signatures (``cosine_similarity``, ``OptimizedRanker``,
 * ``np.argsort(-cosine_scores)`` + rank lookup    -> ``ss_rank_order``      (reference :225-235)
 * ``OptimizedRanker.top_k(query, chunks, k)`` (new) -> fused cosine + top-k (K1/K2), no score vector
 
-BM25 (lexical), the RRF sum and the percentile labelling stay on the host (SURVEY.md section 8f,
+BM25 (lexical) stays on the host; ``rank_query_groups_batched`` fuses the RRF sum, the fused order and the
+percentile thresholds of a whole block of query groups into one launch (``ss_segmented_rank_rrf``); the
+per-query API keeps the RRF sum and the labelling on the host (SURVEY.md section 8f,
 rank 3): they are O(N) bookkeeping on per-query groups.  Equal scores rank lower-index-first where
 the reference's non-stable ``argsort`` leaves the order unspecified.
 """
@@ -198,6 +200,51 @@ class OptimizedRanker:
         return out.sort_values(by="rrf_score", ascending=False).reset_index(drop=True)
 
 
+def rank_query_groups_batched(ranker: "OptimizedRanker", groups: List[tuple], upper_percentile: float = 80,
+                              lower_percentile: float = 20, text_column: str = "chunk_text"):
+    """Device-batched form of the per-query loop (reference :488-536 calling :201-250 and :517-526).
+
+    ``groups`` = ``[(query_text, chunks_df), ...]``.  Embeddings (cached encoder) and BM25 stay per group on the
+    host; cosine scores, both rank lookups, the RRF sum, the fused order and the two percentile thresholds
+    of ALL groups come from one ``ss_segmented_rank_rrf`` launch.  Returns one
+    ``(ranked_df, pos_threshold, neg_threshold)`` per group, ``ranked_df`` exactly as
+    ``rank_single_query_optimized`` builds it (ties: lower row first)."""
+    import torch
+    from .. import similarity
+    if not groups:
+        return []
+    q_rows, c_rows, bm_rows, sizes = [], [], [], []
+    for query, df in groups:
+        if text_column not in df.columns:
+            raise ValueError(f"Text column '{text_column}' not found in DataFrame")
+        chunks = df[text_column].fillna("").tolist()
+        q_rows.append(np.asarray(ranker.get_query_embedding(query), dtype=np.float32).reshape(-1))
+        c_rows.append(np.ascontiguousarray(ranker.get_chunk_embeddings_batch(chunks), dtype=np.float32))
+        bm25 = BM25Okapi([c.lower().split() for c in chunks], epsilon=0.25)
+        bm_rows.append(np.maximum(bm25.get_scores(query.lower().split()), 0.0))
+        sizes.append(len(chunks))
+    if max(sizes) > 8192:
+        raise ValueError("a query group holds more than 8192 chunks; rank it with rank_single_query_optimized")
+    offsets = np.zeros(len(sizes) + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum(sizes)
+    out = similarity.segmented_rank_rrf(
+        torch.from_numpy(np.concatenate(c_rows, axis=0)).cuda(), torch.from_numpy(offsets).cuda(),
+        torch.from_numpy(np.stack(q_rows)).cuda(), torch.from_numpy(np.concatenate(bm_rows).astype(np.float32)).cuda(),
+        k_rrf=60.0, upper_percentile=float(upper_percentile), lower_percentile=float(lower_percentile), max_group_rows=max(sizes))
+    cos, rrf = out["cosine"].cpu().numpy(), out["rrf"].cpu().numpy()
+    order, thr = out["order"].cpu().numpy(), out["thresholds"].cpu().numpy()
+    results = []
+    for gi, (_query, df) in enumerate(groups):
+        a, b = int(offsets[gi]), int(offsets[gi + 1])
+        ranked = df.copy()
+        ranked["cosine_score"] = cos[a:b]
+        ranked["bm25_score"] = bm_rows[gi]
+        ranked["rrf_score"] = rrf[a:b]
+        ranked = ranked.iloc[order[a:b]].reset_index(drop=True)
+        results.append((ranked, float(thr[gi, 0]), float(thr[gi, 1])))
+    return results
+
+
 def _label_group(ranked: pd.DataFrame, upper_percentile: int, lower_percentile: int) -> Optional[pd.DataFrame]:
     """Reference :517-526 — keep rows at or above P_upper (label 1) or at or below P_lower (label 0)."""
     scores = ranked["rrf_score"].to_numpy(dtype=float)
@@ -213,9 +260,21 @@ def _process_queries_sequential(df: pd.DataFrame, model_name: str, upper_percent
     """Reference :488-536.  One ranker (one encoder, one CUDA context) serves every query group."""
     ranker = OptimizedRanker(model_name=model_name)
     kept = []
-    for query_id, group in df.groupby("query_id"):
-        if len(group) < 2:
-            continue
+    groups = [(qid, group) for qid, group in df.groupby("query_id") if len(group) >= 2]
+    batched = [(qid, group) for qid, group in groups if len(group) <= 8192]
+    single = [(qid, group) for qid, group in groups if len(group) > 8192]
+    try:
+        # every query group of the block in one device launch
+        ranked_all = rank_query_groups_batched(ranker, [(str(g["query_text"].iloc[0]), g) for _qid, g in batched],
+                                               upper_percentile, lower_percentile)
+        for ranked, pos_thr, neg_thr in ranked_all:
+            sel = ranked[(ranked["rrf_score"] >= pos_thr) | (ranked["rrf_score"] <= neg_thr)].copy()
+            if not sel.empty:
+                sel["label"] = (sel["rrf_score"] >= pos_thr).astype(int)
+                kept.append(sel)
+    except RuntimeError:
+        raise  # CUDA / embedding failures are not swallowed: there is no CPU fallback
+    for query_id, group in single:
         try:
             ranked = ranker.rank_single_query_optimized(str(group["query_text"].iloc[0]), group)
             labelled = None if ranked.empty else _label_group(ranked, upper_percentile, lower_percentile)

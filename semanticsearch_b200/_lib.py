@@ -37,6 +37,8 @@ _SIGNATURES = {
     "ss_cosine_scores": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "ss_rank_order_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "ss_rank_order": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "ss_segmented_rank_rrf": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double, c_double,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ss_topk_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
     "ss_peer_buffer_bytes": (c_size_t, [c_int, c_int, c_int]),

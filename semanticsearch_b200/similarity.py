@@ -186,6 +186,45 @@ def rank_order(scores: torch.Tensor):
     return order, rank1
 
 
+def segmented_rank_rrf(chunks: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, bm25: Optional[torch.Tensor] = None,
+                       k_rrf: float = 60.0, upper_percentile: float = 80.0, lower_percentile: float = 20.0,
+                       max_group_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """Ranking of every query group of a block in one launch (Tool/rank_chunks_optimized.py:215-250,518-519).
+
+    ``chunks`` fp32 ``[rows, d]`` (groups concatenated), ``offsets`` int32 ``[G + 1]`` on the device, ``queries``
+    fp32 ``[G, d]``, ``bm25`` fp32 ``[rows]`` (host-computed lexical scores) or None.  Returns device tensors:
+    ``cosine`` fp32, ``rank_cosine`` / ``rank_bm25`` int32 (1-based inside the group), ``rrf`` fp64, ``order`` int32
+    (local rows by fused score, best first) and ``thresholds`` fp64 ``[G, 2]`` (upper, lower percentile of rrf)."""
+    dev = _require_cuda(chunks, offsets, queries)
+    if chunks.dtype != torch.float32 or queries.dtype != torch.float32 or not chunks.is_contiguous() or not queries.is_contiguous():
+        raise ValueError("chunks and queries must be contiguous float32 tensors")
+    if offsets.dtype != torch.int32 or offsets.dim() != 1 or offsets.numel() != queries.shape[0] + 1:
+        raise ValueError("offsets must be an int32 [groups + 1] tensor")
+    if chunks.shape[1] != queries.shape[1]:
+        raise ValueError("chunks and queries differ in dimension")
+    rows, d = chunks.shape
+    g = queries.shape[0]
+    if max_group_rows is None:
+        max_group_rows = int((offsets[1:] - offsets[:-1]).max().item()) if g else 0
+    if bm25 is not None and (bm25.dtype != torch.float32 or bm25.numel() != rows or not bm25.is_cuda):
+        raise ValueError("bm25 must be a CUDA float32 tensor with one score per chunk row")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        out = {"cosine": torch.empty(rows, dtype=torch.float32, device=dev),
+               "rank_cosine": torch.empty(rows, dtype=torch.int32, device=dev),
+               "rank_bm25": torch.empty(rows, dtype=torch.int32, device=dev) if bm25 is not None else None,
+               "rrf": torch.empty(rows, dtype=torch.float64, device=dev),
+               "order": torch.empty(rows, dtype=torch.int32, device=dev),
+               "thresholds": torch.empty((g, 2), dtype=torch.float64, device=dev)}
+        st = lib.ss_segmented_rank_rrf(chunks.data_ptr(), d, offsets.data_ptr(), g, max(1, int(max_group_rows)), queries.data_ptr(),
+                                       bm25.data_ptr() if bm25 is not None else None, float(k_rrf), float(upper_percentile),
+                                       float(lower_percentile), out["cosine"].data_ptr(), out["rank_cosine"].data_ptr(),
+                                       out["rank_bm25"].data_ptr() if bm25 is not None else None, out["rrf"].data_ptr(),
+                                       out["order"].data_ptr(), out["thresholds"].data_ptr(), _stream_ptr(dev))
+        _lib.check(st, "ss_segmented_rank_rrf")
+    return out
+
+
 def topk_merge(keys: torch.Tensor, k_out: Optional[int] = None):
     """Merge ``keys[P, B, k]`` (P best-first lists per query) into the global top ``k_out``.
 

@@ -115,3 +115,71 @@ def test_rank_and_filter_end_to_end(tmp_path):
         assert R.rank_and_filter_chunks_optimized(str(tmp_path / "missing.tsv"), tmp_path, str(orig)) == ""
     finally:
         emb.set_embedding_backend(None)
+
+
+def test_segmented_rank_rrf_matches_numpy():
+    """K8 against the reference expressions (rank_chunks_optimized.py:215-250,518-519) evaluated with numpy on
+    the same inputs: cosine within 1e-5, ranks / fused scores / order / percentile thresholds exact given the
+    kernel's own cosine values (ties -> lower row first)."""
+    from semanticsearch_b200 import similarity
+    rng = np.random.default_rng(12)
+    sizes = [2, 3, 40, 257, 1000, 1, 64, 5000]
+    d = 96
+    C = rng.standard_normal((sum(sizes), d)).astype(np.float32)
+    Q = rng.standard_normal((len(sizes), d)).astype(np.float32)
+    bm = np.maximum(rng.standard_normal(sum(sizes)), 0.0).astype(np.float32)   # many exact zeros: ties
+    C[5] = 0.0
+    C[50] = C[49]                                                                # duplicate chunk: cosine tie
+    off = np.zeros(len(sizes) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(sizes)
+    out = similarity.segmented_rank_rrf(torch.from_numpy(C).cuda(), torch.from_numpy(off).cuda(), torch.from_numpy(Q).cuda(),
+                                        torch.from_numpy(bm).cuda(), upper_percentile=80, lower_percentile=20)
+    torch.cuda.synchronize()
+    cos, rc, rb = out["cosine"].cpu().numpy(), out["rank_cosine"].cpu().numpy(), out["rank_bm25"].cpu().numpy()
+    rrf, order, thr = out["rrf"].cpu().numpy(), out["order"].cpu().numpy(), out["thresholds"].cpu().numpy()
+    for g, n in enumerate(sizes):
+        a, b = off[g], off[g + 1]
+        want_cos = ro.cosine_similarity_ref(Q[g:g + 1], C[a:b])[0]
+        np.testing.assert_allclose(cos[a:b], want_cos, atol=1e-5, rtol=0)
+        for scores, ranks in ((cos[a:b], rc[a:b]), (bm[a:b], rb[a:b])):
+            lookup = np.empty(n, dtype=np.int64)
+            lookup[ro.rank_order_ref(scores)] = np.arange(1, n + 1)              # np.argsort(-s) + rank lookup, stable ties
+            np.testing.assert_array_equal(ranks, lookup)
+        want_rrf = 1.0 / (60 + rc[a:b].astype(np.float64)) + 1.0 / (60 + rb[a:b].astype(np.float64))
+        np.testing.assert_array_equal(rrf[a:b], want_rrf)                        # bit-exact fp64
+        np.testing.assert_array_equal(order[a:b], np.argsort(-want_rrf, kind="stable"))
+        assert thr[g, 0] == np.percentile(want_rrf, 80) and thr[g, 1] == np.percentile(want_rrf, 20)
+
+
+def test_batched_group_ranking_equals_per_query_path():
+    from semanticsearch_b200.Tool import Sentence_Embedding as emb
+    from semanticsearch_b200.Tool import rank_chunks_optimized as R
+    rng = np.random.default_rng(3)
+    table, groups = {}, []
+    for q in range(4):
+        table[f"query text {q} words"] = rng.standard_normal(48).astype(np.float32)
+        rows = []
+        for c in range(30 + 7 * q):
+            t = f"q{q} chunk {c} words {c % 4} text"
+            table[t] = rng.standard_normal(48).astype(np.float32)
+            rows.append({"query_id": f"Q{q}", "chunk_id": f"Q{q}_c{c}", "chunk_text": t})
+        groups.append((f"query text {q} words", pd.DataFrame(rows)))
+    emb.set_embedding_backend(lambda text_list, model_name, batch_size=32, device_preference=None:
+                              np.stack([table[t] for t in text_list]).astype(np.float32))
+    try:
+        ranker = R.OptimizedRanker(model_name="m", device_preference="cuda", cache_size=100000)
+        batched = R.rank_query_groups_batched(ranker, groups, 80, 20)
+        for (query, df), (ranked, pos_thr, neg_thr) in zip(groups, batched):
+            single = ranker.rank_single_query_optimized(query, df)
+            assert list(ranked.columns) == list(single.columns)
+            a = ranked.set_index("chunk_id").loc[df["chunk_id"]]
+            b = single.set_index("chunk_id").loc[df["chunk_id"]]
+            np.testing.assert_allclose(a["cosine_score"].to_numpy(), b["cosine_score"].to_numpy(), atol=1e-6, rtol=0)
+            np.testing.assert_array_equal(a["bm25_score"].to_numpy(), b["bm25_score"].to_numpy())
+            np.testing.assert_allclose(a["rrf_score"].to_numpy(), b["rrf_score"].to_numpy(), rtol=1e-12)
+            assert np.all(np.diff(ranked["rrf_score"].to_numpy()) <= 0)
+            labelled = R._label_group(single, 80, 20)
+            sel = ranked[(ranked["rrf_score"] >= pos_thr) | (ranked["rrf_score"] <= neg_thr)]
+            assert sorted(sel["chunk_id"]) == sorted(labelled["chunk_id"])
+    finally:
+        emb.set_embedding_backend(None)
