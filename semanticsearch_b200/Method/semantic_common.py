@@ -95,11 +95,18 @@ def similarity_matrices_from_embeddings(doc_embeddings: Sequence[np.ndarray]) ->
     if not live:
         return out
     dim = int(doc_embeddings[live[0]].shape[1])
-    rows = [np.ascontiguousarray(doc_embeddings[d], dtype=np.float32) for d in live]
+    on_device = all(isinstance(doc_embeddings[d], torch.Tensor) and doc_embeddings[d].is_cuda for d in live)
+    if on_device:
+        # embedding hand-off: encoder outputs that already live in HBM
+        # (SentenceTransformer.encode(convert_to_tensor=True)) skip the numpy round trip of reference :107-114
+        rows = [doc_embeddings[d].to(torch.float32) for d in live]
+    else:
+        rows = [np.ascontiguousarray(doc_embeddings[d].cpu().numpy() if isinstance(doc_embeddings[d], torch.Tensor)
+                                     else doc_embeddings[d], dtype=np.float32) for d in live]
     if any(r.shape[1] != dim for r in rows):
         raise ValueError("all documents of one batch must share the embedding dimension")
     plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
-    E = torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
+    E = torch.cat(rows, dim=0).contiguous() if on_device else torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
     S = ragged.segmented_simmatrix(E, plan).cpu().numpy()
     for slot, d in enumerate(live):
         n = sizes[d]

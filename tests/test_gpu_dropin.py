@@ -135,3 +135,17 @@ def test_splitter_dropin_reproduces_reference_groups(golden_dir, fake_text_stack
         assert [c[0] for c in out] == [f"doc_{name}_chunk{i}" for i in range(len(m["groups"]))]
         for (cid, _t, mj), grp in zip(out, m["groups"]):
             assert json.loads(mj)["n"] == grp[1] - grp[0] + 1
+
+
+def test_similarity_matrices_accept_device_embeddings():
+    """Embedding hand-off: CUDA tensors in, same matrices out as for numpy input."""
+    import torch
+    from semanticsearch_b200.Method import semantic_common as sc
+    rng = np.random.default_rng(9)
+    docs = [rng.standard_normal((n, 384)).astype(np.float32) for n in (5, 130, 1, 40)]
+    host = sc.similarity_matrices_from_embeddings(docs)
+    dev = sc.similarity_matrices_from_embeddings([torch.from_numpy(d).cuda() for d in docs])
+    assert host[2] is None and dev[2] is None
+    for a, b in zip(host, dev):
+        if a is not None:
+            np.testing.assert_array_equal(a, b)
