@@ -1,0 +1,54 @@
+"""CPU-only checks of host-side planning and dispatch logic (no kernel launches)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_plan128_unit_table_enumerates_upper_triangular_tiles():
+    from semanticsearch_b200 import _lib
+    lib = _lib.load()
+    sizes = [0, 1, 128, 129, 300, 512, 513]
+    offsets = np.zeros(len(sizes) + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum(sizes)
+    total = ctypes.c_int64()
+    assert lib.ss_segmented_plan128_host(offsets.ctypes.data, len(sizes), None, 0, ctypes.byref(total)) == 0
+    want = []
+    for d, n in enumerate(sizes):
+        T = (n + 127) // 128
+        want += [(d, i, j, 0) for i in range(T) for j in range(i, T)]
+    assert total.value == len(want)
+    units = np.zeros((len(want), 4), dtype=np.int32)
+    assert lib.ss_segmented_plan128_host(offsets.ctypes.data, len(sizes), units.ctypes.data, len(want), ctypes.byref(total)) == 0
+    assert [tuple(u) for u in units.tolist()] == want
+    # a table that is too small is refused, decreasing offsets are refused
+    assert lib.ss_segmented_plan128_host(offsets.ctypes.data, len(sizes), units.ctypes.data, 3, ctypes.byref(total)) != 0
+    bad = np.array([0, 5, 3], dtype=np.int32)
+    assert lib.ss_segmented_plan128_host(bad.ctypes.data, 2, None, 0, ctypes.byref(total)) != 0
+
+
+def test_choose_algo_dispatch_rules():
+    from semanticsearch_b200 import similarity as sim
+    C16 = torch.zeros((1000, 768), dtype=torch.bfloat16)
+    C32 = torch.zeros((1000, 768), dtype=torch.float32)
+    q = lambda b, dt=torch.bfloat16: torch.zeros((b, 768), dtype=dt)
+    assert sim.choose_algo(C16, q(1), 10) == "stream"
+    assert sim.choose_algo(C16, q(2), 10) == "tcstream"
+    assert sim.choose_algo(C16, q(16), 100) == "tcstream"          # BASELINE config 5
+    assert sim.choose_algo(C16, q(sim.GEMM_MIN_BATCH - 1), 10) == "tcstream"
+    assert sim.choose_algo(C16, q(4096), 10) == "gemm"             # BASELINE config 4b
+    assert sim.choose_algo(C16, q(4096), 100) == "tcstream"        # k > 16: pooled top-k, several corpus passes
+    assert sim.choose_algo(C16, q(4096), 2000) == "stream"         # beyond K7's k limit
+    assert sim.choose_algo(C32, q(100, torch.float32), 10) == "stream"   # fp32 keeps the 1e-5 bound on CUDA cores
+    assert sim.choose_algo(C16, q(8, torch.float16), 10) == "stream"     # mixed dtypes
+    odd = torch.zeros((1000, 100), dtype=torch.bfloat16)
+    assert sim.choose_algo(odd, torch.zeros((8, 100), dtype=torch.bfloat16), 10) == "stream"  # rows not 16-byte multiples
+
+
+def test_operators_refuse_cpu_tensors():
+    from semanticsearch_b200 import ragged, similarity
+    with pytest.raises(RuntimeError, match="CUDA"):
+        similarity.segmented_rank_rrf(torch.zeros((4, 8)), torch.zeros(2, dtype=torch.int32), torch.zeros((1, 8)))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ragged.adjacent_cosine(torch.zeros((4, 8)))
