@@ -424,7 +424,8 @@ static GemmPlan make_gemm_plan(long long n_rows, int n_queries) {
   const int cg = gemm_cta_group(n_queries);
   g.n_qb = (n_queries + G_BM * cg - 1) / (G_BM * cg);
   g.n_tiles = (n_rows + G_BN - 1) / G_BN;
-  const long long target_units = static_cast<long long>(sm_count() / cg) * 8;
+  static const int units_per_worker = getenv("SS_GEMM_UNITS_PER_WORKER") ? std::max(1, atoi(getenv("SS_GEMM_UNITS_PER_WORKER"))) : 8;
+  const long long target_units = static_cast<long long>(sm_count() / cg) * units_per_worker;
   long long n_chunks = std::max<long long>(1, (target_units + g.n_qb - 1) / g.n_qb);
   n_chunks = std::min<long long>(n_chunks, std::max<long long>(1, g.n_tiles / 8));  // at least ~8 tiles per chunk
   g.tiles_per_chunk = static_cast<int>((g.n_tiles + n_chunks - 1) / n_chunks);
