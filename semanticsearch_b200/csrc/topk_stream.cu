@@ -12,6 +12,7 @@
 //   warps' lists and writes k keys per query; ss_topk_merge() folds the per-CTA lists.
 // The score matrix never exists in memory; the corpus is read exactly once per query group.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ss_common.cuh"
@@ -441,6 +442,11 @@ struct StreamConfig {
 static size_t list_bytes(int warps, int bt, int kpad) { return static_cast<size_t>(warps) * bt * kpad * 8; }
 static int rows_per_iter_for(int bt) { return bt <= 2 ? 4 : (bt == 4 ? 3 : 2); }
 
+static int small_corpus_ctas_per_sm() {
+  static const int v = getenv("SS_STREAM_SMALL_CTAS") ? std::max(1, atoi(getenv("SS_STREAM_SMALL_CTAS"))) : 1;
+  return v;
+}
+
 static bool make_config(const void* corpus, long long n_rows, int dim, int dtype, int n_queries, int k,
                         StreamConfig* cfg) {
   const size_t es = dtype_size(dtype);
@@ -470,10 +476,10 @@ static bool make_config(const void* corpus, long long n_rows, int dim, int dtype
       cfg->n_tiles = (n_rows + tile_rows - 1) / tile_rows;
       cfg->grid_y = (n_queries + bt - 1) / bt;
       // Several query groups (grid.y) share the SMs: with a small corpus a full-width grid per group
-      // only multiplies prologue / epilogue / merge work, so aim at ~2 CTAs per SM in total.
+      // only multiplies prologue / epilogue / merge work (measured on config 1: 0.94 ms full width, 0.43 ms at one CTA per SM in total).
       long long gx = std::min<long long>(sms, cfg->n_tiles);
       if (cfg->grid_y > 1 && cfg->n_tiles < 8LL * sms)
-        gx = std::min<long long>(gx, std::max<long long>(1, (2LL * sms + cfg->grid_y - 1) / cfg->grid_y));
+        gx = std::min<long long>(gx, std::max<long long>(1, (static_cast<long long>(small_corpus_ctas_per_sm()) * sms + cfg->grid_y - 1) / cfg->grid_y));
       cfg->grid_x = static_cast<int>(std::max<long long>(1, gx));
       cfg->threads = kStreamThreads;
       cfg->smem = fixed + static_cast<size_t>(stages) * tile_bytes;
