@@ -80,6 +80,17 @@ size_t ss_rank_order_workspace_bytes(int n_queries, int64_t n);
 int ss_rank_order(const float* scores, int n_queries, int64_t n, void* workspace, size_t workspace_bytes,
                   int32_t* out_order, int32_t* out_rank1, void* stream);
 
+/* ---- K9: cosine + top-k for many queries over a small (L2-resident) corpus ------------------------
+ * Same contract as ss_cosine_topk_stream (any dtype, any dim, k <= 4096) for the reference's own scale
+ * (BASELINE.json config 1: 100 queries x 10 000 chunks x 384 fp32): a 64 x 64-tile fp32 score kernel writes
+ * the n_queries x n_rows matrix into the workspace, then one CTA per query selects its top k exactly
+ * (3-pass radix select, lowest-index ties, bitonic sort of the k keys).  n_rows <= 2^24. */
+size_t ss_cosine_topk_small_workspace_bytes(int64_t n_rows, int n_queries);
+int ss_cosine_topk_small(const void* corpus, int64_t n_rows, int dim, int corpus_dtype,
+                         const void* queries, int n_queries, int query_dtype, int k, uint32_t index_base,
+                         void* workspace, size_t workspace_bytes,
+                         uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
+
 /* ---- K8: segmented ranking of query groups (cosine, ranks, reciprocal-rank fusion, percentiles) ----
  * For every group g (chunk rows offsets[g]..offsets[g+1] of the fp32 matrix `chunks`, query g of `queries`), in
  * one launch: out_cos = cosine_similarity(q, chunks)[0] (Tool/rank_chunks_optimized.py:215-216);

@@ -34,6 +34,9 @@ _SIGNATURES = {
     "ss_cosine_topk_tcstream_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "ss_cosine_topk_tcstream": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_uint32, c_void_p, c_size_t,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ss_cosine_topk_small_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "ss_cosine_topk_small": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_int, c_uint32, c_void_p, c_size_t,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "ss_cosine_scores": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "ss_rank_order_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "ss_rank_order": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),

@@ -53,3 +53,40 @@ def test_three_kernels_agree_with_oracle(seed):
     if C.shape[0] < k:  # n < k: trailing slots are empty in every kernel
         for s, i in results.values():
             assert np.all(i[:, C.shape[0]:] == -1) and np.all(np.isneginf(s[:, C.shape[0]:]))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_small_corpus_path_matches_oracle_and_stream_kernel(seed):
+    """K9 (score matrix + exact per-query selection) on fp32 / bf16 / fp16 inputs, odd dims, k up to 1500,
+    duplicates and zero rows: the oracle's top-k up to fp64 ties, and K1's results on the same inputs."""
+    from semanticsearch_b200 import similarity
+    rng = np.random.default_rng(2000 + seed)
+    n = int(rng.integers(1, 30000))
+    d = int(rng.integers(1, 400))
+    b = int(rng.choice([9, 16, 33, 100, 257]))
+    k = int(rng.choice([1, 3, 10, 64, 100, 1000, 1500]))
+    dtype = [torch.float32, torch.bfloat16, torch.float16][seed % 3]
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    C = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((b, d)).astype(np.float32)
+    if n > 10:
+        C[rng.integers(0, n)] = 0.0
+        src, dst = rng.integers(0, n, size=2)
+        C[dst] = C[src]
+        Q[0] = C[src] * 0.5
+        Q[1] = 0.0                                        # zero query: every score 0, lowest rows win
+    Ct = torch.from_numpy(C).cuda().to(dtype).contiguous()
+    Qt = torch.from_numpy(Q).cuda().to(dtype).contiguous()
+    s, i = similarity.cosine_topk(Ct, Qt, k, algo="small", index_base=7)
+    torch.cuda.synchronize()
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    kk = min(k, n)
+    assert np.all(i[:, kk:] == -1) and np.all(np.isneginf(s[:, kk:]))
+    Cr, Qr = Ct.float().cpu().numpy(), Qt.float().cpu().numpy()
+    assert ro.check_topk_against_oracle(Qr, Cr, s[:, :kk], i[:, :kk] - 7, kk, tol) == []
+    if n > 10:
+        assert list(i[1, :min(kk, 5)] - 7) == list(range(min(kk, 5)))
+    if k <= 1024:
+        s1, i1 = similarity.cosine_topk(Ct, Qt, k, algo="stream", index_base=7)
+        np.testing.assert_allclose(s1.cpu().numpy()[:, :kk], s[:, :kk], atol=2e-6, rtol=0)
+        assert (i1.cpu().numpy()[:, :kk] == i[:, :kk]).mean() > 0.98

@@ -39,8 +39,13 @@ def test_choose_algo_dispatch_rules():
     assert sim.choose_algo(C16, q(sim.GEMM_MIN_BATCH - 1), 10) == "tcstream"
     assert sim.choose_algo(C16, q(4096), 10) == "gemm"             # BASELINE config 4b
     assert sim.choose_algo(C16, q(4096), 100) == "tcstream"        # k > 16: pooled top-k, several corpus passes
-    assert sim.choose_algo(C16, q(4096), 2000) == "stream"         # beyond K7's k limit
-    assert sim.choose_algo(C32, q(100, torch.float32), 10) == "stream"   # fp32 keeps the 1e-5 bound on CUDA cores
+    assert sim.choose_algo(C16, q(4096), 2000) == "small"          # beyond K7's k limit, corpus small: score matrix + selection
+    huge16 = torch.zeros((1 << 18, 8), dtype=torch.bfloat16)
+    assert sim.choose_algo(huge16, torch.zeros((4096, 8), dtype=torch.bfloat16), 2000) == "stream"
+    assert sim.choose_algo(C32, q(100, torch.float32), 10) == "small"    # BASELINE config 1 scale: score matrix + selection
+    assert sim.choose_algo(C32, q(8, torch.float32), 10) == "stream"     # one K1 query group
+    big32 = torch.zeros((1 << 18, 8), dtype=torch.float32)
+    assert sim.choose_algo(big32, torch.zeros((100, 8)), 10) == "stream"  # fp32 keeps the 1e-5 bound on CUDA cores
     assert sim.choose_algo(C16, q(8, torch.float16), 10) == "stream"     # mixed dtypes
     odd = torch.zeros((1000, 100), dtype=torch.bfloat16)
     assert sim.choose_algo(odd, torch.zeros((8, 100), dtype=torch.bfloat16), 10) == "stream"  # rows not 16-byte multiples
