@@ -285,6 +285,153 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tiny documents (n <= 32 sentences — three quarters of the reference corpus, median 10): one WARP per
+// document, lane r owns row r of S in registers.  Same arithmetic and outputs as the CTA kernel below,
+// without its fixed costs (2048-bin histograms, block barriers, shared-memory sorts).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallMaxN = 32;
+constexpr int kSmallWarps = 8;
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// value (fp32 bit pattern of a positive float) with at least `want` positive entries >= it, i.e. the want-th largest
+__device__ __forceinline__ uint32_t small_select_desc(const uint32_t (&o)[kSmallMaxN], int n, int want) {
+  uint32_t t = 0u;
+#pragma unroll 1
+  for (int bit = 30; bit >= 0; --bit) {
+    const uint32_t cand = t | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kSmallMaxN; ++j) c += (j < n && o[j] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= want) t = cand;
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(kSmallWarps * 32) group_threshold_small_kernel(const GroupParams p) {
+  const int lane = threadIdx.x & 31;
+  const int doc = blockIdx.x * kSmallWarps + (threadIdx.x >> 5);
+  if (doc >= p.n_docs) return;
+  const int row_base = p.offsets[doc];
+  const int n = p.offsets[doc + 1] - row_base;
+  if (n < 1 || n > kSmallMaxN) return;  // empty and larger documents belong to the CTA kernel
+  const float* S = p.S + p.s_offsets[doc];
+  float* sharp = p.sharp + p.s_offsets[doc];
+  const bool live = lane < n;
+  const double nn = static_cast<double>(n) * n;
+
+  int kk;
+  if (p.knn_mode == 0) kk = max(5, min(32, static_cast<int>(rint(static_cast<double>(n) * 0.06))));
+  else if (p.knn_mode > 0) kk = p.knn_mode;
+  else kk = max(5, min(20, n - 1));
+  const int k_eff = max(1, min(kk, n - 1));
+  const int width = min(min(k_eff + 1, n), kKnnWidth);
+
+  float x[kSmallMaxN];
+  double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < kSmallMaxN; ++j) {
+    x[j] = (live && j < n) ? S[lane * n + j] : 0.f;
+    const double d = static_cast<double>(x[j]);
+    s1 += d;
+    s2 += d * d;
+  }
+  s1 = warp_sum_f64(s1);
+  s2 = warp_sum_f64(s2);
+  const double mean = s1 / nn;
+  const float mu = static_cast<float>(mean);
+  const float sigma = static_cast<float>(sqrt(fmax(s2 / nn - mean * mean, 0.0))) + 1e-9f;
+  const float zscale = 1.4426950408889634f / (sigma * p.tau);
+
+  uint32_t o[kSmallMaxN];  // bit pattern of the positive sharpened values, 0 = not a "positive value"
+  double rs = 0.0, pos_s1 = 0.0, pos_s2 = 0.0;
+  int pos_cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kSmallMaxN; ++j) {
+    float v = 0.f;
+    if (live && j < n) {
+      v = __frcp_rn(1.0f + exp2f(-((x[j] - mu) * zscale)));  // same expression as the CTA kernel's row pass
+      if (j == lane) v = 0.f;
+      sharp[lane * n + j] = v;
+      rs += static_cast<double>(v);
+    }
+    x[j] = v;
+    o[j] = v > 0.f ? __float_as_uint(v) : 0u;
+    if (v > 0.f) {
+      pos_s1 += static_cast<double>(v);
+      pos_s2 += static_cast<double>(v) * static_cast<double>(v);
+      ++pos_cnt;
+    }
+  }
+  if (live) p.centrality[row_base + lane] = static_cast<double>(static_cast<float>(rs) / static_cast<float>(max(n - 1, 1)));
+  pos_s1 = warp_sum_f64(pos_s1);
+  pos_s2 = warp_sum_f64(pos_s2);
+  const int m = __reduce_add_sync(0xffffffffu, pos_cnt);
+  const double m_d = static_cast<double>(m);
+
+  // quantiles of the positive values: numpy's linear interpolation between order statistics lo and lo + 1
+  const double qs[kNumQ] = {0.80, 0.65, 0.60};
+  double q_out[kNumQ] = {0.0, 0.0, 0.0};
+  if (m > 0) {
+#pragma unroll 1
+    for (int t = 0; t < kNumQ; ++t) {
+      const double vi = __dmul_rn(static_cast<double>(m - 1), qs[t]);
+      const double fl = floor(vi);
+      const int lo = static_cast<int>(fl);
+      const double gamma = __dsub_rn(vi, fl);
+      const uint32_t vlo = small_select_desc(o, n, m - lo);            // ascending rank lo == (m - lo)-th largest
+      const uint32_t vhi = (lo + 1 < m) ? small_select_desc(o, n, m - lo - 1) : vlo;
+      q_out[t] = np_lerp(static_cast<double>(__uint_as_float(vlo)), static_cast<double>(__uint_as_float(vhi)), gamma);
+    }
+  }
+
+  // row `lane`: its `width` best neighbours, value descending / index ascending, by successive maxima on registers
+  if (live) {
+    int* oi = p.knn_idx + static_cast<size_t>(row_base + lane) * kKnnWidth;
+    float* ov = p.knn_val + static_cast<size_t>(row_base + lane) * kKnnWidth;
+    uint64_t prev = ~0ull;
+#pragma unroll 1
+    for (int sidx = 0; sidx < width; ++sidx) {
+      uint64_t best = 0ull;
+#pragma unroll
+      for (int j = 0; j < kSmallMaxN; ++j) {
+        const uint64_t key = (static_cast<uint64_t>(float_to_ordered(x[j])) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(j));
+        if (j < n && key < prev && key > best) best = key;
+      }
+      oi[sidx] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(best & 0xFFFFFFFFull));
+      ov[sidx] = ordered_to_float(static_cast<uint32_t>(best >> 32));
+      prev = best;
+    }
+    for (int sidx = width; sidx < kKnnWidth; ++sidx) {
+      oi[sidx] = -1;
+      ov[sidx] = 0.f;
+    }
+  }
+  if (lane == 0) {
+    double* st = p.doc_stats + static_cast<size_t>(doc) * 8;
+    st[0] = static_cast<double>(mu);
+    st[1] = static_cast<double>(sigma);
+    st[2] = q_out[0];
+    st[3] = q_out[1];
+    st[4] = q_out[2];
+    double sd = 0.0;
+    if (m > 0) {
+      const double pm = pos_s1 / m_d;
+      sd = sqrt(fmax(pos_s2 / m_d - pm * pm, 0.0));
+    }
+    st[5] = 0.1 * sd;
+    st[6] = m_d;
+    st[7] = static_cast<double>(kk);
+  }
+}
+
 __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const GroupParams p) {
   __shared__ double red[kGrpWarps];
   __shared__ unsigned int hist[kNumQ][kRadixBins];
@@ -301,6 +448,7 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
     if (threadIdx.x < 8) st[threadIdx.x] = 0.0;
     return;
   }
+  if (n <= kSmallMaxN) return;  // handled by group_threshold_small_kernel (one warp per document)
   const float* S = p.S + p.s_offsets[doc];
   float* sharp = p.sharp + p.s_offsets[doc];
   const long long nn = static_cast<long long>(n) * n;
@@ -628,6 +776,7 @@ extern "C" int ss_group_threshold_pass(const float* S, const int32_t* offsets, c
   {
     ProfileScope prof(st);
     group_threshold_kernel<<<n_docs, kGrpThreads, 0, st>>>(p);
+    group_threshold_small_kernel<<<(n_docs + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, 0, st>>>(p);
   }
   SS_CUDA_CHECK(cudaGetLastError());
   return SS_OK;
