@@ -48,19 +48,35 @@ struct SimTcParams {
   float* out;
 };
 
+// Unit table entry {a, b, c, kind}.  kind 0: tile (ti = b, tj = c) of document a.  kind 1: a PACKED window —
+// documents a .. a + b - 1 (each <= 64 rows, c rows in total, <= 128) share one diagonal tile: their rows
+// are contiguous in memory, the MMA computes the whole window's Gram matrix and the epilogue keeps only
+// each document's own block.  Three quarters of the reference corpus are documents of <= 32 sentences.
 struct SimUnit {
-  int row_base, n, ti, tj;
+  int row_base, n, ti, tj;  // packed: n = rows of the window, ti = tj = 0
   long long s_off;
+  int packed, first_doc, n_docs;
 };
 
 __device__ __forceinline__ SimUnit load_unit(const SimTcParams& p, long long u) {
   const int4 e = __ldg(p.units + u);
   SimUnit r;
   r.row_base = __ldg(p.offsets + e.x);
-  r.n = __ldg(p.offsets + e.x + 1) - r.row_base;
-  r.s_off = __ldg(p.s_offsets + e.x);
-  r.ti = e.y;
-  r.tj = e.z;
+  r.packed = e.w;
+  r.first_doc = e.x;
+  if (e.w) {
+    r.n = e.z;
+    r.n_docs = e.y;
+    r.ti = 0;
+    r.tj = 0;
+    r.s_off = 0;
+  } else {
+    r.n = __ldg(p.offsets + e.x + 1) - r.row_base;
+    r.n_docs = 1;
+    r.s_off = __ldg(p.s_offsets + e.x);
+    r.ti = e.y;
+    r.tj = e.z;
+  }
   return r;
 }
 
@@ -90,7 +106,10 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
   unsigned char* tiles = smem;                                                       // [S_STAGES][64 KB]
   float* scratch = reinterpret_cast<float*>(tiles + S_STAGES * S_STAGE_BYTES);      // [4 warps][32][33] transpose staging
   float* inv_s = scratch + 4 * 32 * 33;                                              // [2][256]: 1/|row| of the A rows, then the B rows
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(inv_s + 2 * 256);
+  long long* row_base_s = reinterpret_cast<long long*>(inv_s + 2 * 256);             // [128] per tile row: offset of (row, window col 0)
+  int* row_lo = reinterpret_cast<int*>(row_base_s + 128);                             // [128] first / one-past-last window column it may write
+  int* row_hi = row_lo + 128;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(row_hi + 128);
   uint64_t* ready_bar = full_bar + S_STAGES;
   uint64_t* empty_bar = ready_bar + S_STAGES;
   uint64_t* tmem_full = empty_bar + S_STAGES;
@@ -196,11 +215,17 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
     uint32_t ph = 0, acc_ph = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int4 e = __ldg(p.units + u);
-      const int n_doc = __ldg(p.offsets + e.x + 1) - __ldg(p.offsets + e.x);
-      // diagonal tiles have no separate B rows; rows past the end of the document (the tile is padded with
-      // whatever follows in memory) feed only outputs that are never written, so they are not split either
-      const int blk = srow < 128 ? e.y : e.z;
-      const bool active = (srow < 128 || e.y != e.z) && (blk * S_BM + r < n_doc);
+      // diagonal tiles have no separate B rows; rows past the end of the document / packed window (the tile
+      // is padded with whatever follows in memory) feed only outputs that are never written, so they are
+      // not split either
+      bool active;
+      if (e.w) {
+        active = srow < 128 && r < e.z;
+      } else {
+        const int n_doc = __ldg(p.offsets + e.x + 1) - __ldg(p.offsets + e.x);
+        const int blk = srow < 128 ? e.y : e.z;
+        active = (srow < 128 || e.y != e.z) && (blk * S_BM + r < n_doc);
+      }
       float ssq0 = 0.f, ssq1 = 0.f;
       for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(&full_bar[s], ph);
@@ -248,11 +273,39 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const SimUnit un = load_unit(p, u);
       const bool diag = un.ti == un.tj;
-      const int n = un.n;
-      float* S = p.out + un.s_off;
-      const int gr = un.ti * S_BM + row;          // this thread's global row inside the document
-      const int gc0 = un.tj * S_BM;
-      const int ncols = min(S_BM, n - gc0);
+      const int ncols = min(S_BM, un.n - un.tj * S_BM);
+      // Per row of the tile: the window-local column range [c_lo, c_hi) it may write, the element offset of
+      // (row, window column 0) for the direct tile, and offset + leading dimension for the transposed tile.
+      int c_lo = 0, c_hi = 0, ld = 1;
+      long long rbase = 0, mbase = 0;
+      if (!un.packed) {
+        const int gr = un.ti * S_BM + row;  // this thread's row inside the document
+        if (gr < un.n) {
+          c_hi = ncols;
+          ld = un.n;
+          rbase = un.s_off + static_cast<long long>(gr) * un.n + un.tj * S_BM;
+          mbase = un.s_off + static_cast<long long>(un.tj) * S_BM * un.n + gr;
+        }
+      } else if (row < un.n) {
+        int lo_d = un.first_doc, hi_d = un.first_doc + un.n_docs;  // last document with offsets[d] <= global row
+        const int grow = un.row_base + row;
+        while (hi_d - lo_d > 1) {
+          const int mid = (lo_d + hi_d) >> 1;
+          if (__ldg(p.offsets + mid) <= grow) lo_d = mid; else hi_d = mid;
+        }
+        const int d_lo = __ldg(p.offsets + lo_d) - un.row_base;
+        const int d_n = __ldg(p.offsets + lo_d + 1) - __ldg(p.offsets + lo_d);
+        const long long d_off = __ldg(p.s_offsets + lo_d);
+        c_lo = d_lo;
+        c_hi = d_lo + d_n;
+        ld = d_n;
+        rbase = d_off + static_cast<long long>(row - d_lo) * d_n - d_lo;
+        mbase = d_off - static_cast<long long>(d_lo) * d_n + (row - d_lo);
+      }
+      row_lo[(warp - 2) * 32 + lane] = c_lo;
+      row_hi[(warp - 2) * 32 + lane] = c_hi;
+      row_base_s[(warp - 2) * 32 + lane] = rbase;
+      __syncwarp();
       mbar_wait(&norm_full[acc], acc_ph);
       const float* inv_a = inv_s + acc * 256;
       const float* inv_b = diag ? inv_a : inv_a + 128;
@@ -278,11 +331,11 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
         }
         // transposed tile S[col][row]: lanes hold consecutive rows -> consecutive addresses.  Diagonal
         // tiles mirror their strict upper triangle so that S is bit-for-bit symmetric.
-        if (gr < n) {
+        if (c_hi > c_lo) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int gc = gc0 + c0 + j;
-            if (gc < n && (!diag || gc > gr)) S[static_cast<size_t>(gc) * n + gr] = x[j];
+            const int c = c0 + j;
+            if (c >= c_lo && c < c_hi && (!diag || c > row)) p.out[mbase + static_cast<long long>(c) * ld] = x[j];
           }
         }
         // direct tile S[row][col]: transpose 32 x 32 through padded shared memory so that lanes
@@ -290,12 +343,12 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
 #pragma unroll
         for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = x[j];
         __syncwarp();
-        const int gc = gc0 + c0 + lane;
+        const int c = c0 + lane;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int grj = un.ti * S_BM + quad * 32 + j;
+          const int rj = (warp - 2) * 32 + j;
           const float y = scr[j * 33 + lane];
-          if (grj < n && gc < n && (!diag || gc >= grj)) S[static_cast<size_t>(grj) * n + gc] = y;
+          if (c >= row_lo[rj] && c < row_hi[rj] && (!diag || c >= quad * 32 + j)) p.out[row_base_s[rj] + c] = y;
         }
         __syncwarp();
       }
@@ -326,23 +379,49 @@ using namespace ss;
 extern "C" int ss_segmented_plan128_host(const int32_t* offsets_host, int n_docs, int32_t* units_host, int64_t capacity_units,
                                          int64_t* total_units) {
   if (!offsets_host || n_docs < 0) return fail(SS_ERR_INVALID_ARG, "ss_segmented_plan128_host: bad arguments");
+  constexpr int kPackMaxDoc = 64;  // documents up to this many rows are packed into shared 128-row windows
   int64_t t = 0;
-  for (int d = 0; d < n_docs; ++d) {
+  auto emit = [&](int a, int b, int c, int kind) -> bool {
+    if (units_host) {
+      if (t >= capacity_units) return false;
+      units_host[4 * t + 0] = a;
+      units_host[4 * t + 1] = b;
+      units_host[4 * t + 2] = c;
+      units_host[4 * t + 3] = kind;
+    }
+    ++t;
+    return true;
+  };
+  int d = 0;
+  while (d < n_docs) {
     const int64_t n = static_cast<int64_t>(offsets_host[d + 1]) - offsets_host[d];
     if (n < 0) return fail(SS_ERR_INVALID_ARG, "ss_segmented_plan128_host: offsets must be non-decreasing");
-    const int T = static_cast<int>((n + S_BM - 1) / S_BM);
-    for (int ti = 0; ti < T; ++ti) {
-      for (int tj = ti; tj < T; ++tj) {
-        if (units_host) {
-          if (t >= capacity_units) return fail(SS_ERR_WORKSPACE, "ss_segmented_plan128_host: unit table too small");
-          units_host[4 * t + 0] = d;
-          units_host[4 * t + 1] = ti;
-          units_host[4 * t + 2] = tj;
-          units_host[4 * t + 3] = 0;
-        }
-        ++t;
+    if (n <= kPackMaxDoc) {
+      // greedy window of consecutive small documents (their rows are contiguous)
+      int d1 = d;
+      int64_t rows = 0;
+      while (d1 < n_docs) {
+        const int64_t m = static_cast<int64_t>(offsets_host[d1 + 1]) - offsets_host[d1];
+        if (m < 0) return fail(SS_ERR_INVALID_ARG, "ss_segmented_plan128_host: offsets must be non-decreasing");
+        if (m > kPackMaxDoc || rows + m > S_BM) break;
+        rows += m;
+        ++d1;
       }
+      if (rows > 0) {
+        if (d1 - d == 1) {
+          if (!emit(d, 0, 0, 0)) return fail(SS_ERR_WORKSPACE, "ss_segmented_plan128_host: unit table too small");
+        } else if (!emit(d, d1 - d, static_cast<int>(rows), 1)) {
+          return fail(SS_ERR_WORKSPACE, "ss_segmented_plan128_host: unit table too small");
+        }
+      }
+      d = d1;
+      continue;
     }
+    const int T = static_cast<int>((n + S_BM - 1) / S_BM);
+    for (int ti = 0; ti < T; ++ti)
+      for (int tj = ti; tj < T; ++tj)
+        if (!emit(d, ti, tj, 0)) return fail(SS_ERR_WORKSPACE, "ss_segmented_plan128_host: unit table too small");
+    ++d;
   }
   if (total_units) *total_units = t;
   return SS_OK;
@@ -370,7 +449,7 @@ extern "C" int ss_segmented_simmatrix_tc(const float* rows, int64_t total_rows, 
   p.dim = dim;
   p.nkb = (dim + S_BK - 1) / S_BK;
   p.out = out_S;
-  const size_t smem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + 4 * 32 * 33 * 4 + 2 * 256 * 4 + 256;
+  const size_t smem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + 4 * 32 * 33 * 4 + 2 * 256 * 4 + 128 * (8 + 4 + 4) + 256;
   cudaError_t e = cudaFuncSetAttribute(segmented_simmatrix_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e == cudaSuccess) {
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(sm_count(), n_units)));

@@ -88,3 +88,29 @@ def test_tc_adversarial_magnitudes():
     np.testing.assert_allclose(S, _fp64(E), atol=TOL, rtol=0)
     assert abs(S[3, 10] - 1.0) < 6e-6 and abs(S[3, 11] + 1.0) < 6e-6
     assert np.all(S[12] == 0)
+
+
+def test_tc_packed_windows_of_small_documents():
+    """Documents of <= 64 sentences share 128-row tiles (the reference corpus: median 10 sentences): every
+    document's block must come out exactly as if it had a tile of its own — symmetric, zero rows zero,
+    nothing written across document boundaries."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(41)
+    sizes = [int(x) for x in np.clip(np.rint(rng.lognormal(np.log(10.0), 1.2, size=300)), 1, 200)] + [0, 64, 64, 1, 0, 2, 63, 65, 0]
+    rows = _docs(rng, sizes, 384)
+    rows[5][0] = 0.0
+    E = np.concatenate([r for r in rows if r.shape[0] > 0], axis=0)
+    plan = ragged.make_plan(sizes, "cuda")
+    S = torch.full((plan.total_s + 7,), float("nan"), dtype=torch.float32, device="cuda")   # canary past the end
+    ragged.segmented_simmatrix(torch.from_numpy(E).cuda(), plan, out=S, algo="tc")
+    torch.cuda.synchronize()
+    Sh = S.cpu().numpy()
+    assert np.all(np.isnan(Sh[plan.total_s:])) and not np.any(np.isnan(Sh[: plan.total_s]))
+    for d, n in enumerate(sizes):
+        if n == 0:
+            continue
+        blk = Sh[plan.s_offsets[d]:plan.s_offsets[d + 1]].reshape(n, n)
+        np.testing.assert_array_equal(blk, blk.T)
+        np.testing.assert_allclose(blk, _fp64(rows[d]), atol=TOL, rtol=0)
+    blk5 = Sh[plan.s_offsets[5]:plan.s_offsets[6]].reshape(sizes[5], sizes[5])
+    assert np.all(blk5[0] == 0)

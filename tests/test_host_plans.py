@@ -6,23 +6,45 @@ import pytest
 import torch
 
 
-def test_plan128_unit_table_enumerates_upper_triangular_tiles():
+def _expected_units(sizes):
+    """Host restatement of the 128-tile plan: consecutive documents of <= 64 rows share packed windows of
+    <= 128 rows (kind 1: first doc, doc count, rows); everything else is upper-triangular 128 x 128 tiles."""
+    want, d = [], 0
+    while d < len(sizes):
+        if sizes[d] <= 64:
+            d1, rows = d, 0
+            while d1 < len(sizes) and sizes[d1] <= 64 and rows + sizes[d1] <= 128:
+                rows += sizes[d1]
+                d1 += 1
+            if rows > 0:
+                want.append((d, 0, 0, 0) if d1 - d == 1 else (d, d1 - d, rows, 1))
+            d = d1
+            continue
+        T = (sizes[d] + 127) // 128
+        want += [(d, i, j, 0) for i in range(T) for j in range(i, T)]
+        d += 1
+    return want
+
+
+def test_plan128_unit_table_tiles_and_packed_windows():
     from semanticsearch_b200 import _lib
     lib = _lib.load()
-    sizes = [0, 1, 128, 129, 300, 512, 513]
+    for sizes in ([0, 1, 128, 129, 300, 512, 513], [10, 20, 64, 64, 1, 0, 0, 5, 65, 3, 120, 7, 7, 7], [0, 0], [64, 65, 64]):
+        offsets = np.zeros(len(sizes) + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum(sizes)
+        total = ctypes.c_int64()
+        assert lib.ss_segmented_plan128_host(offsets.ctypes.data, len(sizes), None, 0, ctypes.byref(total)) == 0
+        want = _expected_units(sizes)
+        assert total.value == len(want)
+        units = np.zeros((max(len(want), 1), 4), dtype=np.int32)
+        assert lib.ss_segmented_plan128_host(offsets.ctypes.data, len(sizes), units.ctypes.data, len(want), ctypes.byref(total)) == 0
+        assert [tuple(u) for u in units[: len(want)].tolist()] == want
+    # a table that is too small is refused, decreasing offsets are refused
+    sizes = [0, 1, 128, 129, 300]
     offsets = np.zeros(len(sizes) + 1, dtype=np.int32)
     offsets[1:] = np.cumsum(sizes)
+    units = np.zeros((64, 4), dtype=np.int32)
     total = ctypes.c_int64()
-    assert lib.ss_segmented_plan128_host(offsets.ctypes.data, len(sizes), None, 0, ctypes.byref(total)) == 0
-    want = []
-    for d, n in enumerate(sizes):
-        T = (n + 127) // 128
-        want += [(d, i, j, 0) for i in range(T) for j in range(i, T)]
-    assert total.value == len(want)
-    units = np.zeros((len(want), 4), dtype=np.int32)
-    assert lib.ss_segmented_plan128_host(offsets.ctypes.data, len(sizes), units.ctypes.data, len(want), ctypes.byref(total)) == 0
-    assert [tuple(u) for u in units.tolist()] == want
-    # a table that is too small is refused, decreasing offsets are refused
     assert lib.ss_segmented_plan128_host(offsets.ctypes.data, len(sizes), units.ctypes.data, 3, ctypes.byref(total)) != 0
     bad = np.array([0, 5, 3], dtype=np.int32)
     assert lib.ss_segmented_plan128_host(bad.ctypes.data, 2, None, 0, ctypes.byref(total)) != 0
