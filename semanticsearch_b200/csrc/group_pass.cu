@@ -41,7 +41,9 @@ struct GroupParams {
   float* knn_val;        // [total_rows][33]
 };
 
+template <int NT>
 __device__ __forceinline__ double block_sum(double v, double* red) {
+  constexpr int kGrpWarps = NT / 32;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
@@ -156,7 +158,7 @@ struct RowCtx {
 __device__ __forceinline__ unsigned int lin_bin(float v) { return min(2047u, static_cast<unsigned int>(v * 2048.0f)); }
 
 // One warp per row with the row held in NREG registers per lane (n <= 32 * NREG).
-template <int NREG>
+template <int NREG, int kGrpWarps>
 __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int lane, double& pos_s1, double& pos_s2,
                                               unsigned int& pos_cnt) {
   const float* S = cx.S;
@@ -301,27 +303,23 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 }
 
 // value (fp32 bit pattern of a positive float) with at least `want` positive entries >= it, i.e. the want-th largest
-__device__ __forceinline__ uint32_t small_select_desc(const uint32_t (&o)[kSmallMaxN], int n, int want) {
+template <int NMAX>
+__device__ __forceinline__ uint32_t small_select_desc(const uint32_t (&o)[NMAX], int n, int want) {
   uint32_t t = 0u;
 #pragma unroll 1
-  for (int bit = 30; bit >= 0; --bit) {
+  for (int bit = 29; bit >= 0; --bit) {  // sharpened values are <= 1.0f = 0x3F800000: bits 31 and 30 are never set
     const uint32_t cand = t | (1u << bit);
     int c = 0;
 #pragma unroll
-    for (int j = 0; j < kSmallMaxN; ++j) c += (j < n && o[j] >= cand) ? 1 : 0;
+    for (int j = 0; j < NMAX; ++j) c += (j < n && o[j] >= cand) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
     if (c >= want) t = cand;
   }
   return t;
 }
 
-__global__ void __launch_bounds__(kSmallWarps * 32) group_threshold_small_kernel(const GroupParams p) {
-  const int lane = threadIdx.x & 31;
-  const int doc = blockIdx.x * kSmallWarps + (threadIdx.x >> 5);
-  if (doc >= p.n_docs) return;
-  const int row_base = p.offsets[doc];
-  const int n = p.offsets[doc + 1] - row_base;
-  if (n < 1 || n > kSmallMaxN) return;  // empty and larger documents belong to the CTA kernel
+template <int NMAX>
+__device__ __forceinline__ void group_small_doc(const GroupParams& p, int doc, int row_base, int n, int lane) {
   const float* S = p.S + p.s_offsets[doc];
   float* sharp = p.sharp + p.s_offsets[doc];
   const bool live = lane < n;
@@ -334,10 +332,10 @@ __global__ void __launch_bounds__(kSmallWarps * 32) group_threshold_small_kernel
   const int k_eff = max(1, min(kk, n - 1));
   const int width = min(min(k_eff + 1, n), kKnnWidth);
 
-  float x[kSmallMaxN];
+  float x[NMAX];
   double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-  for (int j = 0; j < kSmallMaxN; ++j) {
+  for (int j = 0; j < NMAX; ++j) {
     x[j] = (live && j < n) ? S[lane * n + j] : 0.f;
     const double d = static_cast<double>(x[j]);
     s1 += d;
@@ -350,11 +348,11 @@ __global__ void __launch_bounds__(kSmallWarps * 32) group_threshold_small_kernel
   const float sigma = static_cast<float>(sqrt(fmax(s2 / nn - mean * mean, 0.0))) + 1e-9f;
   const float zscale = 1.4426950408889634f / (sigma * p.tau);
 
-  uint32_t o[kSmallMaxN];  // bit pattern of the positive sharpened values, 0 = not a "positive value"
+  uint32_t o[NMAX];  // bit pattern of the positive sharpened values, 0 = not a "positive value"
   double rs = 0.0, pos_s1 = 0.0, pos_s2 = 0.0;
   int pos_cnt = 0;
 #pragma unroll
-  for (int j = 0; j < kSmallMaxN; ++j) {
+  for (int j = 0; j < NMAX; ++j) {
     float v = 0.f;
     if (live && j < n) {
       v = __frcp_rn(1.0f + exp2f(-((x[j] - mu) * zscale)));  // same expression as the CTA kernel's row pass
@@ -386,8 +384,22 @@ __global__ void __launch_bounds__(kSmallWarps * 32) group_threshold_small_kernel
       const double fl = floor(vi);
       const int lo = static_cast<int>(fl);
       const double gamma = __dsub_rn(vi, fl);
-      const uint32_t vlo = small_select_desc(o, n, m - lo);            // ascending rank lo == (m - lo)-th largest
-      const uint32_t vhi = (lo + 1 < m) ? small_select_desc(o, n, m - lo - 1) : vlo;
+      const uint32_t vlo = small_select_desc<NMAX>(o, n, m - lo);      // ascending rank lo == (m - lo)-th largest
+      uint32_t vhi = vlo;
+      if (lo + 1 < m) {  // order statistic lo + 1: vlo again if its duplicates reach that rank, else the next larger value
+        int c_gt = 0;
+        uint32_t above = 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+          if (j < n && o[j] > vlo) {
+            ++c_gt;
+            above = min(above, o[j]);
+          }
+        }
+        c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+        above = __reduce_min_sync(0xffffffffu, above);
+        if (c_gt > m - lo - 2) vhi = above;
+      }
       q_out[t] = np_lerp(static_cast<double>(__uint_as_float(vlo)), static_cast<double>(__uint_as_float(vhi)), gamma);
     }
   }
@@ -401,7 +413,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) group_threshold_small_kernel
     for (int sidx = 0; sidx < width; ++sidx) {
       uint64_t best = 0ull;
 #pragma unroll
-      for (int j = 0; j < kSmallMaxN; ++j) {
+      for (int j = 0; j < NMAX; ++j) {
         const uint64_t key = (static_cast<uint64_t>(float_to_ordered(x[j])) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(j));
         if (j < n && key < prev && key > best) best = key;
       }
@@ -432,7 +444,24 @@ __global__ void __launch_bounds__(kSmallWarps * 32) group_threshold_small_kernel
   }
 }
 
-__global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const GroupParams p) {
+__global__ void __launch_bounds__(kSmallWarps * 32) group_threshold_small_kernel(const GroupParams p) {
+  const int lane = threadIdx.x & 31;
+  const int doc = blockIdx.x * kSmallWarps + (threadIdx.x >> 5);
+  if (doc >= p.n_docs) return;
+  const int row_base = p.offsets[doc];
+  const int n = p.offsets[doc + 1] - row_base;
+  if (n < 1 || n > kSmallMaxN) return;  // empty and larger documents belong to the CTA kernels
+  if (n <= 8) group_small_doc<8>(p, doc, row_base, n, lane);
+  else if (n <= 16) group_small_doc<16>(p, doc, row_base, n, lane);
+  else group_small_doc<32>(p, doc, row_base, n, lane);
+}
+
+// NT = 512 threads for documents of more than 128 sentences, 128 threads for 33..128: a mid-size document
+// keeps only a few warps busy, and every block barrier costs the idle ones.
+template <int NT>
+__global__ void __launch_bounds__(NT) group_threshold_kernel(const GroupParams p, int n_min, int n_max) {
+  constexpr int kGrpThreads = NT;
+  constexpr int kGrpWarps = NT / 32;
   __shared__ double red[kGrpWarps];
   __shared__ unsigned int hist[kNumQ][kRadixBins];
   __shared__ uint64_t knn_scr[kGrpWarps][64];
@@ -449,6 +478,7 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
     return;
   }
   if (n <= kSmallMaxN) return;  // handled by group_threshold_small_kernel (one warp per document)
+  if (n < n_min || n > n_max) return;  // the other block size's share
   const float* S = p.S + p.s_offsets[doc];
   float* sharp = p.sharp + p.s_offsets[doc];
   const long long nn = static_cast<long long>(n) * n;
@@ -489,8 +519,8 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
     s2 = t2[0] + t2[1];
   }
   for (int i = tid; i < kRadixBins; i += kGrpThreads) hist[0][i] = 0u;  // pass-0 histogram (shared by the three targets)
-  s1 = block_sum(s1, red);
-  s2 = block_sum(s2, red);
+  s1 = block_sum<NT>(s1, red);
+  s2 = block_sum<NT>(s2, red);
   if (tid == 0) {
     const double mean = s1 / static_cast<double>(nn);
     const double var = fmax(s2 / static_cast<double>(nn) - mean * mean, 0.0);
@@ -509,10 +539,10 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
     cx.S = S; cx.sharp = sharp; cx.n = n; cx.row_base = row_base; cx.width = width;
     cx.mu = mu; cx.sigma = sigma; cx.tau = tau; cx.hist = hist[0]; cx.scr = knn_scr[warp];
     cx.centrality = p.centrality; cx.knn_idx = p.knn_idx; cx.knn_val = p.knn_val;
-    if (n <= 128) row_pass_regs<4>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
-    else if (n <= 256) row_pass_regs<8>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
-    else if (n <= 384) row_pass_regs<12>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
-    else row_pass_regs<16>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    if (n <= 128) row_pass_regs<4, kGrpWarps>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    else if (n <= 256) row_pass_regs<8, kGrpWarps>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    else if (n <= 384) row_pass_regs<12, kGrpWarps>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    else row_pass_regs<16, kGrpWarps>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
   } else {
     // Generic path for very long documents: rows are re-read from memory.
     for (int r = warp; r < n; r += kGrpWarps) {
@@ -572,9 +602,9 @@ __global__ void __launch_bounds__(kGrpThreads) group_threshold_kernel(const Grou
       }
     }
   }
-  pos_s1 = block_sum(pos_s1, red);
-  pos_s2 = block_sum(pos_s2, red);
-  const double m_d = block_sum(static_cast<double>(pos_cnt), red);
+  pos_s1 = block_sum<NT>(pos_s1, red);
+  pos_s2 = block_sum<NT>(pos_s2, red);
+  const double m_d = block_sum<NT>(static_cast<double>(pos_cnt), red);
   const unsigned int m = static_cast<unsigned int>(m_d + 0.5);
   __syncthreads();  // sharp[] and the pass-0 histogram written by this CTA are visible to the whole CTA
 
@@ -775,7 +805,8 @@ extern "C" int ss_group_threshold_pass(const float* S, const int32_t* offsets, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     ProfileScope prof(st);
-    group_threshold_kernel<<<n_docs, kGrpThreads, 0, st>>>(p);
+    group_threshold_kernel<512><<<n_docs, 512, 0, st>>>(p, 129, 0x7fffffff);
+    group_threshold_kernel<128><<<n_docs, 128, 0, st>>>(p, kSmallMaxN + 1, 128);
     group_threshold_small_kernel<<<(n_docs + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, 0, st>>>(p);
   }
   SS_CUDA_CHECK(cudaGetLastError());
