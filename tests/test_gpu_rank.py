@@ -141,3 +141,21 @@ def test_full_size_properties_2M_rows():
     rs, ri = torch.topk(ref, k, dim=1)
     assert torch.allclose(rs, s, atol=LOWP_TOL)
     assert (ri == i).float().mean().item() >= 0.9
+
+
+def test_graphed_search_replays_the_eager_search():
+    """sharded.GraphedSearch (one CUDA-graph launch per search) must return what ShardedCorpus.search returns,
+    for every kernel family, across several replays with different queries."""
+    from semanticsearch_b200.sharded import GraphedSearch, ShardedCorpus
+    g = torch.Generator(device="cuda").manual_seed(5)
+    C = torch.randn((60000, 384), generator=g, device="cuda").to(torch.bfloat16)
+    corpus = ShardedCorpus(C, 1000)
+    for batch, k in ((1, 10), (16, 100), (200, 10)):
+        gs = GraphedSearch(corpus, batch, k)
+        for _ in range(3):
+            Q = torch.randn((batch, 384), generator=g, device="cuda").to(torch.bfloat16)
+            s0, i0 = corpus.search(Q, k)
+            s1, i1 = gs(Q)
+            torch.cuda.synchronize()
+            assert torch.equal(i0, i1) and torch.equal(s0, s1)
+            assert int(i1.min()) >= 1000
