@@ -1,3 +1,4 @@
+"""One grouping-threshold-pass run on documents of lo..hi sentences (ncu driver): python benchmarks/k4_probe_one.py LO HI DOCS"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
