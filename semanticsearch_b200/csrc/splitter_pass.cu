@@ -224,20 +224,111 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n2) {
   }
 }
 
-// One CTA per document.  Shared: keys[n2] (u64) + vals[n2] (double).
-__global__ void __launch_bounds__(128) segmented_percentile_kernel(float* __restrict__ adj, const int* __restrict__ offsets,
-                                                                   int n_docs, double q, int n2_max,
-                                                                   double* __restrict__ out_thr, unsigned char* __restrict__ out_flags,
-                                                                   double* __restrict__ out_stats, float* __restrict__ out_smooth) {
-  extern __shared__ __align__(16) unsigned char pct_smem[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(pct_smem);
-  double* base = reinterpret_cast<double*>(keys + n2_max);
-  __shared__ double s_med;
-  const int doc = blockIdx.x;
+
+// ------------------------------------------------------------------------------------------------
+// Short documents (at most 33 sentences = 32 adjacent pairs — most of the reference corpus): one WARP per
+// document, one pair per lane, order statistics from a shuffle bitonic sort.  Same arithmetic and outputs
+// as the CTA kernel below.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPctSmallWarps = 8;
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+  const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// ascending sort of one key per lane
+__device__ __forceinline__ uint64_t warp_sort_asc_u64(uint64_t v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = shfl_u64(v, lane ^ j);
+      const bool up = (lane & k) == 0;           // this block sorts ascending
+      const bool lower = (lane & j) == 0;        // this lane keeps the smaller key of an ascending pair
+      const bool take_min = lower == up;
+      v = take_min ? (v < o ? v : o) : (v > o ? v : o);
+    }
+  }
+  return v;
+}
+// np.quantile (linear) / np.median on the warp-sorted keys (lane i holds order statistic i); all lanes get the result
+__device__ __forceinline__ double warp_quantile(uint64_t sorted, int m, double q) {
+  const double vi = __dmul_rn(static_cast<double>(m - 1), q);
+  const double fl = floor(vi);
+  int lo = static_cast<int>(fl);
+  lo = max(0, min(lo, m - 1));
+  const int hi = min(lo + 1, m - 1);
+  const double g = __dsub_rn(vi, fl);
+  const double a = ordered_to_f64(shfl_u64(sorted, lo)), b = ordered_to_f64(shfl_u64(sorted, hi));
+  const double diff = __dsub_rn(b, a);
+  double r = __dadd_rn(a, __dmul_rn(diff, g));
+  if (g >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, g)));
+  return r;
+}
+__device__ __forceinline__ double warp_median(uint64_t sorted, int m) {
+  if (m & 1) return ordered_to_f64(shfl_u64(sorted, m / 2));
+  return __dadd_rn(ordered_to_f64(shfl_u64(sorted, m / 2 - 1)), ordered_to_f64(shfl_u64(sorted, m / 2))) / 2.0;
+}
+
+__global__ void __launch_bounds__(kPctSmallWarps * 32) segmented_percentile_small_kernel(
+    float* __restrict__ adj, const int* __restrict__ offsets, int n_docs, double q, double* __restrict__ out_thr,
+    unsigned char* __restrict__ out_flags, double* __restrict__ out_stats, float* __restrict__ out_smooth) {
+  const int lane = threadIdx.x & 31;
+  const int doc = blockIdx.x * kPctSmallWarps + (threadIdx.x >> 5);
   if (doc >= n_docs) return;
+  const int a0 = offsets[doc], a1 = offsets[doc + 1];
+  const int m = a1 - a0 - 1;  // adjacent pairs
+  if (m < 1 || m > 32) return;  // 0/1-sentence and longer documents belong to the CTA kernel
+  const bool live = lane < m;
+  const float x = live ? adj[a0 + lane] : 0.f;
+  const double d = 1.0 - static_cast<double>(x);
+  const uint64_t sorted = warp_sort_asc_u64(live ? f64_to_ordered(d) : ~0ull, lane);
+  const double thr = warp_quantile(sorted, m, q);
+  if (lane == 0) {
+    out_thr[doc] = thr;
+    adj[a1 - 1] = 0.f;  // the slot of a document's last sentence held a cross-document cosine
+    if (out_flags) out_flags[a1 - 1] = 0;
+    if (out_smooth) out_smooth[a1 - 1] = 0.f;
+  }
+  if (out_flags && live) out_flags[a0 + lane] = d > thr ? 1 : 0;
+  if (!out_stats && !out_smooth) return;
+  // median-of-3 smoothing with edge replication (Splitter:340-356); unchanged if m < 3
+  double v = static_cast<double>(x);
+  {
+    const float xl = __shfl_sync(0xffffffffu, x, max(lane - 1, 0));
+    const float xr = __shfl_sync(0xffffffffu, x, min(lane + 1, m - 1));
+    if (m >= 3) {
+      const double l = static_cast<double>(xl), r = static_cast<double>(xr);
+      v = fmax(fmin(l, v), fmin(fmax(l, v), r));
+    }
+  }
+  if (out_smooth && live) out_smooth[a0 + lane] = static_cast<float>(v);
+  if (!out_stats) return;
+  const uint64_t s2 = warp_sort_asc_u64(live ? f64_to_ordered(v) : ~0ull, lane);
+  const double med = warp_median(s2, m);
+  const double p25 = warp_quantile(s2, m, 0.25), p75 = warp_quantile(s2, m, 0.75);
+  const uint64_t s3 = warp_sort_asc_u64(live ? f64_to_ordered(fabs(v - med)) : ~0ull, lane);
+  const double mad = warp_median(s3, m) + 1e-9;
+  if (lane == 0) {
+    double* st = out_stats + static_cast<size_t>(doc) * 4;
+    st[0] = med;
+    st[1] = mad;
+    st[2] = p25;
+    st[3] = p75;
+  }
+}
+
+// One CTA per document.  Shared: keys[n2] (u64) + vals[n2] (double).
+__device__ __forceinline__ void percentile_doc(float* __restrict__ adj, const int* __restrict__ offsets, int doc, double q,
+                                               uint64_t* keys, double* base, double* s_med_p, double* __restrict__ out_thr,
+                                               unsigned char* __restrict__ out_flags, double* __restrict__ out_stats,
+                                               float* __restrict__ out_smooth) {
+  double& s_med = *s_med_p;
   const int a0 = offsets[doc], a1 = offsets[doc + 1];
   const int n = a1 - a0;
   const int m = n - 1;  // adjacent pairs
+  if (m >= 1 && m <= 32) return;  // handled by segmented_percentile_small_kernel (one warp per document)
   if (out_flags)
     for (int i = threadIdx.x; i < n; i += blockDim.x) out_flags[a0 + i] = 0;
   if (out_smooth)
@@ -300,6 +391,18 @@ __global__ void __launch_bounds__(128) segmented_percentile_kernel(float* __rest
   __syncthreads();
   bitonic_sort_smem(keys, n2);
   if (threadIdx.x == 0) out_stats[static_cast<size_t>(doc) * 4 + 1] = np_median_sorted(keys, m) + 1e-9;
+}
+
+// One CTA per document (a persistent, document-striding variant measured slower: long documents unbalance it).
+__global__ void __launch_bounds__(128) segmented_percentile_kernel(float* __restrict__ adj, const int* __restrict__ offsets,
+                                                                   int n_docs, double q, int n2_max,
+                                                                   double* __restrict__ out_thr, unsigned char* __restrict__ out_flags,
+                                                                   double* __restrict__ out_stats, float* __restrict__ out_smooth) {
+  extern __shared__ __align__(16) unsigned char pct_smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(pct_smem);
+  double* base = reinterpret_cast<double*>(keys + n2_max);
+  __shared__ double s_med;
+  if (blockIdx.x < n_docs) percentile_doc(adj, offsets, blockIdx.x, q, keys, base, &s_med, out_thr, out_flags, out_stats, out_smooth);
 }
 
 }  // namespace ss
@@ -372,6 +475,9 @@ extern "C" int ss_segmented_percentile(float* adj, const int32_t* offsets, int n
     return fail(SS_ERR_UNSUPPORTED, "ss_segmented_percentile: documents longer than 8193 sentences are not supported");
   if (smem > 48 * 1024)
     SS_CUDA_CHECK(cudaFuncSetAttribute(segmented_percentile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  segmented_percentile_small_kernel<<<(n_docs + kPctSmallWarps - 1) / kPctSmallWarps, kPctSmallWarps * 32, 0,
+                                      static_cast<cudaStream_t>(stream)>>>(adj, offsets, n_docs, pct / 100.0, out_thr, out_flags, out_stats,
+                                                                           out_smooth);
   segmented_percentile_kernel<<<n_docs, 128, smem, static_cast<cudaStream_t>(stream)>>>(adj, offsets, n_docs, pct / 100.0, n2, out_thr,
                                                                                        out_flags, out_stats, out_smooth);
   SS_CUDA_CHECK(cudaGetLastError());
