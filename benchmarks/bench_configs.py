@@ -250,9 +250,48 @@ def config6(args):
                              "sample": f"{len(sample)} groups: rank_chunks_optimized.py:215-250,518-519 without BM25 scoring"}}
 
 
+def config7(args):
+    """Not a BASELINE.json config: the C99 leg of the splitter — similarity matrix, global
+    rank transform and the greedy divisive cut search (Semantic_Splitter_Optimized.py:169-238) for a batch of documents."""
+    rng = np.random.default_rng(15)
+    D = args.docs or 2000
+    sizes = rng.integers(16, 513, size=D)
+    E = topic_rows(sizes, 384, 16, "cuda")
+    plan = ragged.make_plan(sizes, "cuda")
+    mins = np.maximum(3, np.maximum(5, np.rint(sizes / 50.0))).astype(np.int32)  # c99_min_chunk of the reference (:449-453)
+    S = torch.empty(plan.total_s, dtype=torch.float32, device="cuda")
+    ms_sim = cuda_time(lambda: ragged.segmented_simmatrix(E, plan, out=S), args.steps)
+    ms_rank = cuda_time(lambda: ragged.c99_rank_matrix(S, plan), max(1, args.steps // 2), warmup=1)
+    R = ragged.c99_rank_matrix(S, plan)
+    ms_cut = cuda_time(lambda: ragged.c99_divisive_cuts(R, plan, mins), max(1, args.steps // 2), warmup=1)
+    cuts, n_cuts, _ = ragged.c99_divisive_cuts(R, plan, mins)
+    peak, src = hbm_peak()
+    sat = int(((sizes.astype(np.int64) + 1) ** 2).sum())
+    alg_cut = 4 * plan.total_s + 2 * 8 * sat  # read R, write the float64 table once per pass (two passes)
+    from oracle import splitter_oracle as spo
+    sample = list(range(0, D, max(1, D // 6)))[:6]
+    Eh = [E[plan.offsets[d]:plan.offsets[d + 1]].cpu().numpy() for d in sample]
+    Eh = [(e / np.linalg.norm(e, axis=1, keepdims=True)).astype(np.float32) for e in Eh]
+    t0 = time.perf_counter()
+    for e, d in zip(Eh, sample):
+        spo.c99_divisive_ref(spo.c99_global_rank_ref(spo.c99_similarity_ref(e)), int(mins[d]))
+    cpu_s = (time.perf_counter() - t0) / len(sample)
+    total = ms_sim + ms_rank + ms_cut
+    return {"config": f"c99 (8f-1): {D} docs, n~U[16,512], 384-d fp32: S, global rank matrix, divisive cut search",
+            "metric": "docs/s", "value": D / (total * 1e-3), "ms_simmatrix": ms_sim, "ms_rank": ms_rank, "ms_cuts": ms_cut,
+            "rows": plan.total_rows, "sum_n2": plan.total_s, "mean_cuts_per_doc": float(n_cuts.float().mean().item()),
+            "roofline": {"bound": "hbm", "kernel": "c99_divisive_kernel", "achieved": alg_cut / (ms_cut * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg_cut / (ms_cut * 1e-3) / 1e9 / peak, "peak_source": src,
+                         "algorithmic_bytes_per_launch": alg_cut,
+                         "note": "the search rounds after the table build are latency-bound (one block arg-max per cut)"},
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "docs/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                             "sample": f"{len(sample)} documents (mean n = {float(np.mean([len(e) for e in Eh])):.0f}): "
+                                       f"Semantic_Splitter_Optimized.py:169-238 as restated in oracle/splitter_oracle.py"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True, choices=[1, 2, 3, 5, 6])
+    ap.add_argument("--config", type=int, required=True, choices=[1, 2, 3, 5, 6, 7])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--docs", type=int, default=0)
     ap.add_argument("--rows", type=int, default=0)
@@ -264,7 +303,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
         if args.config not in (2, 3):
             raise SystemExit("multi-GPU runs of this script cover the ragged configs 2 and 3 (bench.py covers 4 and 5)")
-    res = {1: config1, 2: config2, 3: config3, 5: config5, 6: config6}[args.config](args)
+    res = {1: config1, 2: config2, 3: config3, 5: config5, 6: config6, 7: config7}[args.config](args)
     res["data"] = "synthetic"
     res["n_gpus"] = WORLD
     if WORLD > 1:

@@ -217,6 +217,21 @@ int ss_c99_rank_matrix(const float* S, const int32_t* offsets, const int64_t* s_
                        int max_doc_rows, int use_local_rank, int mask_size, int32_t* workspace_rows, float* out_R,
                        void* stream);
 
+/* K10 — C99 divisive cut search on each document's rank matrix R (output layout of ss_c99_rank_matrix):
+ * device form of the greedy loop at Method/Semantic_Splitter_Optimized.py:194-238.  Every round takes the cut
+ * with the largest gain = 0.5 * (mean R[a:c,a:c] + mean R[c:b,c:b]) - mean R[a:b,a:b] over all segments [a, b)
+ * and a+m <= c <= b-m (first best in segment-list order, ascending c), until no candidate is left, max_cuts is
+ * reached, or (stop_by_gain != 0) the gain is below max(min_gain, 0.1 * |mean of that segment|).  Block means
+ * come from a float64 summed-area table (sat_workspace: sum over documents of (n+1)^2 doubles; sat_offsets =
+ * int64[n_docs] start of each table, device).  min_chunk / max_cuts: per-document int32 arrays (device) or
+ * null to use the *_all scalars (max_cuts < 0 = unlimited).  out_cuts[offsets[d] + i] = i-th picked cut of
+ * document d, out_n_cuts[d] = count (0 when n < 2 * min_chunk, :165-166; -1 = min_chunk < 1), out_profile
+ * (nullable) [offsets[d] + i] = inside density after i cuts (D_series, :206,234).  max_doc_rows <= 2048. */
+int ss_c99_divisive_cuts(const float* R, const int32_t* offsets, const int64_t* s_offsets, const int64_t* sat_offsets,
+                         int n_docs, int max_doc_rows, const int32_t* min_chunk, int min_chunk_all, const int32_t* max_cuts,
+                         int max_cuts_all, double min_gain, int stop_by_gain, double* sat_workspace, int32_t* out_cuts,
+                         int32_t* out_n_cuts, double* out_profile, void* stream);
+
 /* ---- K5: semantic-splitter passes over ragged documents ---------------------------------------
  * Documents are concatenated: rows = [total_rows x dim]; offsets = int32[n_docs+1] (device) CSR
  * row offsets.

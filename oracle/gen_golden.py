@@ -160,6 +160,44 @@ def gen_splitter(ref):
     np.savez_compressed(os.path.join(OUT_DIR, "splitter.npz"), **payload)
 
 
+C99_CASES = (
+    # name, n, d, sentences per topic, kwargs of the reference's _c99_boundaries
+    ("c6", 6, 16, 3, {"min_chunk_size": 3}),
+    ("c7", 7, 16, 3, {"min_chunk_size": 3, "min_gain": 0.0}),
+    ("c30", 30, 24, 6, {"min_chunk_size": 3}),
+    ("c30p", 30, 24, 6, {"min_chunk_size": 3, "stopping": "profile"}),
+    ("c64", 64, 24, 9, {"min_chunk_size": 5}),
+    ("c64m2", 64, 24, 9, {"min_chunk_size": 5, "max_cuts": 2}),
+    ("c64m0", 64, 24, 9, {"min_chunk_size": 5, "max_cuts": 0}),
+    ("c64p", 64, 24, 9, {"min_chunk_size": 4, "stopping": "profile", "knee_c": 0.8, "smooth_window": 2}),
+    ("c50l", 50, 24, 8, {"min_chunk_size": 3, "use_local_rank": True, "mask_size": 11}),
+    ("c50lp", 50, 24, 8, {"min_chunk_size": 4, "use_local_rank": True, "mask_size": 7, "stopping": "profile"}),
+    ("c150", 150, 32, 12, {"min_chunk_size": 5}),
+    ("c150g", 150, 32, 12, {"min_chunk_size": 3, "min_gain": 5.0}),
+    ("c300", 300, 32, 14, {"min_chunk_size": 6}),
+    ("c300p", 300, 32, 14, {"min_chunk_size": 6, "stopping": "profile"}),
+)
+
+
+def gen_c99_cuts(ref):
+    """Outputs of the reference's own ``_c99_boundaries`` (Splitter:155-264) with its locals ``R``, ``cuts``
+    (pick order) and ``D_series`` captured at return."""
+    rng = np.random.default_rng(404)
+    payload, meta = {}, {}
+    for name, n, d, spt, kwargs in C99_CASES:
+        E = topic_doc(rng, n, d, sent_per_topic=spt, noise=0.6)
+        En = (E / np.linalg.norm(E, axis=1, keepdims=True)).astype(np.float32)
+        bounds, grabbed = capture_locals(ref.split._c99_boundaries, ("R", "cuts", "D_series"), {"_c99_boundaries"}, En, **kwargs)
+        loc = grabbed.get("_c99_boundaries", {})
+        payload[f"{name}_En"] = En
+        if n <= 64:
+            payload[f"{name}_R"] = np.asarray(loc["R"], dtype=np.float32)
+        payload[f"{name}_D"] = np.asarray(loc.get("D_series", []), dtype=np.float64)
+        meta[name] = {"kwargs": kwargs, "bounds": [int(x) for x in bounds], "cuts": [int(x) for x in loc.get("cuts", [])]}
+    payload["meta_json"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(OUT_DIR, "c99_cuts.npz"), **payload)
+
+
 def main():
     ref = ref_shim.load_reference()
     if ref is None:
@@ -168,6 +206,7 @@ def main():
     gen_rank(ref)
     gen_simmatrix_and_grouping(ref)
     gen_splitter(ref)
+    gen_c99_cuts(ref)
     print("wrote", sorted(os.listdir(OUT_DIR)))
 
 

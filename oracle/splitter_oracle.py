@@ -3,7 +3,7 @@
 Restates the dense arithmetic of Method/Semantic_Splitter_Optimized.py: ``_embed``'s
 normalisation ``:140-152``, adjacent-sentence similarity ``:412``, ``_median_smooth``
 ``:340-356``, the robust MAD/IQR sigmoid ``:417-437`` (+ valley tau ``:465``), and the C99
-similarity / rank matrices ``:169-192``.  BASELINE.json config 3's "95th-percentile
+similarity / rank matrices ``:169-192`` and the divisive cut search on the rank matrix ``:194-264``.  BASELINE.json config 3's "95th-percentile
 breakpoints" has no counterpart in the reference; it is pinned to numpy as
 ``d = 1 - adj``, ``thr = np.percentile(d, 95)``, ``breakpoints = where(d > thr)``.
 """
@@ -114,3 +114,79 @@ def c99_local_rank_ref(S: np.ndarray, mask_size: int = 11) -> np.ndarray:
             win = S[i0:i1, j0:j1]
             R[i, j] = float((win < S[i, j]).sum()) / float(win.size if win.size else 1)
     return R
+
+
+def _block_mean_f32(R: np.ndarray, a: int, b: int, default: float) -> float:
+    """``float(R[a:b, a:b].mean())`` — an fp32 numpy mean widened, as in Splitter:215-222."""
+    blk = R[a:b, a:b]
+    return float(blk.mean()) if blk.size > 0 else default
+
+
+def c99_inside_density_ref(R: np.ndarray, segments) -> float:
+    """Splitter:194-204 — summed fp32 block sums over summed block areas."""
+    tot, area = 0.0, 0
+    for a, b in segments:
+        if b > a:
+            blk = R[a:b, a:b]
+            tot += float(blk.sum()) if blk.size > 0 else 0.0
+            area += (b - a) * (b - a)
+    return tot / float(area) if area > 0 else 0.0
+
+
+def c99_divisive_ref(R: np.ndarray, min_chunk_size: int = 3, max_cuts=None, min_gain: float = 0.01, stopping: str = "gain",
+                     knee_c: float = 1.2, smooth_window: int = 3):
+    """Splitter:205-264 — greedy divisive search.  Returns ``(boundaries, cuts_in_pick_order, D_series)``.
+
+    Every round scans the segment list in list order (a split pops the segment and appends its two halves at
+    the END of the list, :232-233) and every admissible cut ``a+m <= c <= b-m`` in ascending order; strict
+    ``>`` keeps the first best.  ``gain = 0.5 * (mean(left) + mean(right)) - mean(whole)`` with fp32 block
+    means.  Stop: no candidate, ``max_cuts`` reached, or (``stopping == 'gain'``) best gain below
+    ``max(min_gain, 0.1 * |mean(whole of the best segment)|)``.  ``'profile'`` keeps cutting and then keeps
+    the cuts before the first smoothed density increment below ``mean - knee_c * std`` (:239-264).
+    """
+    R = np.asarray(R)
+    n = R.shape[0]
+    m = int(min_chunk_size)
+    if n < 2 * m:
+        return [], [], []
+    mode = stopping.lower()
+    seg_list = [(0, n)]
+    picked = []
+    series = [c99_inside_density_ref(R, seg_list)]
+    while True:
+        top = (-1e9, None, None, 0.0)  # gain, cut, list index, mean of the whole segment
+        for li, (a, b) in enumerate(seg_list):
+            if b - a < 2 * m:
+                continue
+            whole = _block_mean_f32(R, a, b, 0.0)
+            for c in range(a + m, b - m + 1):
+                g = 0.5 * (_block_mean_f32(R, a, c, whole) + _block_mean_f32(R, c, b, whole)) - whole
+                if g > top[0]:
+                    top = (g, c, li, whole)
+        g_best, cut, li, whole = top
+        floor = max(float(min_gain), 0.1 * abs(whole))
+        if cut is None or (max_cuts is not None and len(picked) >= int(max_cuts)):
+            break
+        if mode == "gain" and g_best < floor:
+            break
+        a, b = seg_list.pop(int(li))
+        seg_list.extend([(a, cut), (cut, b)])
+        picked.append(int(cut))
+        series.append(c99_inside_density_ref(R, sorted(seg_list)))
+    if mode != "profile" or not picked:
+        return sorted(set(picked)), picked, series
+    return c99_profile_knee_ref(picked, series, knee_c, smooth_window), picked, series
+
+
+def c99_profile_knee_ref(picked, series, knee_c: float = 1.2, smooth_window: int = 3):
+    """Splitter:241-264 — keep the cuts made before the first sharp drop of the smoothed density increments."""
+    steps = np.diff(np.array(series, dtype=float))
+    if steps.size == 0:
+        return sorted(set(picked))
+    w = max(1, int(smooth_window))
+    sm = np.convolve(steps, np.ones(w, dtype=float) / float(w), mode="same") if (w > 1 and steps.size >= w) else steps
+    limit = float(sm.mean()) - float(knee_c) * float(sm.std() + 1e-9)
+    for i, v in enumerate(sm, start=1):
+        if v < limit:
+            return sorted(set(picked[: min(max(1, i) - 1, len(picked))]))
+    return sorted(set(picked))

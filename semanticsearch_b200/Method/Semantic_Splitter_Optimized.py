@@ -8,10 +8,13 @@ Same public names, signatures and return conventions (``process_sentence_splitti
 * adjacent-sentence cosine + median-of-3 smoothing + median / MAD / P25 / P75   -> K5
 * the C99 similarity matrix and its rank transform                              -> K3 + ss_c99_rank_matrix
 
-while the sequential boundary logic (valley detection, divisive C99 search, voting, NMS, soft cap,
-boundary snapping, short-segment merge; reference :194-338,447-652) is re-implemented on the host
+* the greedy divisive cut search on the rank matrix (reference :194-238)            -> K10 (ss_c99_divisive_cuts)
+
+while the sequential boundary logic (valley detection, the C99 profile knee, voting, NMS, soft cap,
+boundary snapping, short-segment merge; reference :239-338,447-652) is re-implemented on the host
 with the same semantics.  The divisive search evaluates block means through a float64 summed-area
-table instead of one ``ndarray.mean()`` per candidate cut.
+table instead of one ``ndarray.mean()`` per candidate cut; ``c99_boundaries_batch`` runs it for many
+documents at once.
 """
 from __future__ import annotations
 
@@ -95,6 +98,70 @@ def splitter_device_pass(doc_embeddings: Sequence[np.ndarray], pct: float = 95.0
     return out
 
 
+_C99_BATCH_BYTES = 6 << 30  # device bytes one slice of a C99 batch may take (S + R + float64 block-sum table)
+
+
+def c99_boundaries_batch(doc_embeddings: Sequence[np.ndarray], min_chunk_sizes, max_cuts: Optional[int] = None,
+                         min_gain: float = 0.01, *, use_local_rank: bool = False, mask_size: int = 11, stopping: str = "gain",
+                         knee_c: float = 1.2, smooth_window: int = 3) -> List[List[int]]:
+    """``_c99_boundaries`` (reference :155-264) for a batch of documents in three launches per slice: similarity
+    matrices (K3), rank transform, divisive cut search (K10).  Only the picked cuts (and, for
+    ``stopping='profile'``, the density profile) come back to the host.  ``min_chunk_sizes``: one int or one per
+    document.  Documents the device search does not take (more than 2048 sentences, ``min_chunk < 1``) run the
+    host statement of the same search on the device-computed rank matrix."""
+    import torch
+    from .. import ragged
+    n_docs = len(doc_embeddings)
+    mins = [int(min_chunk_sizes)] * n_docs if np.ndim(min_chunk_sizes) == 0 else [int(x) for x in min_chunk_sizes]
+    if len(mins) != n_docs:
+        raise ValueError("min_chunk_sizes must be a scalar or one value per document")
+    mode = str(stopping).lower()
+    out: List[List[int]] = [[] for _ in range(n_docs)]
+    if max_cuts is not None and int(max_cuts) <= 0:
+        return out                                       # :225 stops before the first cut
+    live, slow = [], []
+    for d, e in enumerate(doc_embeddings):
+        n = int(e.shape[0])
+        if n < 2 * mins[d]:
+            continue                                     # :165-166
+        (live if (mins[d] >= 1 and n <= ragged.C99_CUTS_MAX_ROWS) else slow).append(d)
+    for d in slow:
+        R = _c99_rank_on_device(doc_embeddings[d], bool(use_local_rank), int(mask_size))
+        out[d] = _divisive_cuts(R, mins[d], max_cuts, float(min_gain), mode, float(knee_c), int(smooth_window))
+    start = 0
+    while start < len(live):
+        stop, used = start, 0
+        while stop < len(live):
+            n = int(doc_embeddings[live[stop]].shape[0])
+            need = 16 * (n + 1) * (n + 1)
+            if stop > start and used + need > _C99_BATCH_BYTES:
+                break
+            used += need
+            stop += 1
+        ids = live[start:stop]
+        start = stop
+        rows = [np.ascontiguousarray(doc_embeddings[d], dtype=np.float32) for d in ids]
+        plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
+        E = torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
+        S = ragged.segmented_simmatrix(E, plan)
+        R = ragged.c99_rank_matrix(S, plan, use_local_rank=bool(use_local_rank), mask_size=int(mask_size))
+        del S
+        cuts, n_cuts, profile = ragged.c99_divisive_cuts(R, plan, [mins[d] for d in ids], max_cuts, float(min_gain),
+                                                         stop_by_gain=(mode == "gain"), want_profile=(mode == "profile"))
+        cuts_h, n_h = cuts.cpu().numpy(), n_cuts.cpu().numpy()
+        prof_h = profile.cpu().numpy() if profile is not None else None
+        for slot, d in enumerate(ids):
+            base, cnt = int(plan.offsets[slot]), int(n_h[slot])
+            if cnt < 0:
+                raise RuntimeError("ss_c99_divisive_cuts skipped a document it was dispatched for")
+            picked = [int(x) for x in cuts_h[base:base + cnt]]
+            if mode != "profile" or not picked:
+                out[d] = sorted(set(picked))
+            else:
+                out[d] = _profile_knee(picked, prof_h[base:base + cnt + 1], float(knee_c), int(smooth_window))
+    return out
+
+
 def _c99_rank_on_device(embs: np.ndarray, use_local_rank: bool, mask_size: int) -> np.ndarray:
     import torch
     from .. import ragged
@@ -117,10 +184,10 @@ class _BlockSums:
         self.sat = np.zeros((n + 1, n + 1), dtype=np.float64)
         self.sat[1:, 1:] = np.cumsum(np.cumsum(R.astype(np.float64), axis=0), axis=1)
 
-    def mean(self, a: int, b: int) -> float:
-        """Mean of R[a:b, a:b]."""
+    def mean(self, a: int, b: int, default: float = 0.0) -> float:
+        """Mean of R[a:b, a:b]; ``default`` for an empty block (reference :216-217)."""
         if b <= a:
-            return 0.0
+            return default
         s = self.sat
         return float(s[b, b] - s[a, b] - s[b, a] + s[a, a]) / float((b - a) * (b - a))
 
@@ -155,7 +222,7 @@ def _divisive_cuts(R: np.ndarray, min_chunk: int, max_cuts: Optional[int], min_g
                 continue
             mean_all = blocks.mean(a, b)
             for c in range(a + min_chunk, b - min_chunk + 1):
-                gain = 0.5 * (blocks.mean(a, c) + blocks.mean(c, b)) - mean_all
+                gain = 0.5 * (blocks.mean(a, c, mean_all) + blocks.mean(c, b, mean_all)) - mean_all
                 if gain > best_gain:
                     best_gain, best_pos, best_idx, best_mean_all = gain, c, idx, mean_all
         thr = max(float(min_gain), 0.1 * abs(best_mean_all))
@@ -169,6 +236,11 @@ def _divisive_cuts(R: np.ndarray, min_chunk: int, max_cuts: Optional[int], min_g
         profile.append(inside_density(sorted(segs)))
     if stopping.lower() != "profile" or not cuts:
         return sorted(set(cuts))
+    return _profile_knee(cuts, profile, knee_c, smooth_window)
+
+
+def _profile_knee(cuts: List[int], profile, knee_c: float, smooth_window: int) -> List[int]:
+    """Reference :239-264 — keep the cuts picked before the first sharp drop of the smoothed density increments."""
     deltas = np.diff(np.array(profile, dtype=float))
     if deltas.size == 0:
         return sorted(set(cuts))
@@ -186,11 +258,10 @@ def _c99_boundaries(embs: np.ndarray, min_chunk_size: int = 3, max_cuts: Optiona
                     smooth_window: int = 3) -> List[int]:
     """Reference :155-264.  ``embs`` are sentence embeddings (normalised or not: the kernel
     normalises); the similarity matrix and its rank transform are computed on the GPU."""
-    n = embs.shape[0]
-    if n < 2 * int(min_chunk_size):
+    if embs.shape[0] < 2 * int(min_chunk_size):
         return []
-    R = _c99_rank_on_device(embs, bool(use_local_rank), int(mask_size))
-    return _divisive_cuts(R, int(min_chunk_size), max_cuts, float(min_gain), str(stopping), float(knee_c), int(smooth_window))
+    return c99_boundaries_batch([embs], int(min_chunk_size), max_cuts, min_gain, use_local_rank=use_local_rank, mask_size=mask_size,
+                                stopping=stopping, knee_c=knee_c, smooth_window=smooth_window)[0]
 
 
 def _valley_boundaries(adj_sims: List[float], *, triplet_tau: float = 0.12, min_boundary_spacing: int = 2,

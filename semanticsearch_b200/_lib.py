@@ -59,6 +59,8 @@ _SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p]),
     "ss_similarity_distribution": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "ss_c99_rank_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "ss_c99_divisive_cuts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_double, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ss_segmented_adjacent_cosine": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "ss_segmented_percentile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),

@@ -3,10 +3,19 @@
 //   global: R[i,j] = #{k : S[i,k] < S[i,j]} + #{k : S[k,j] < S[i,j]}            (:189-192)
 //   local : R[i,j] = #{(a,b) in the clipped m x m window around (i,j) : S[a,b] < S[i,j]} / window size  (:171-186)
 //
-// Pure compare-and-count (integer work): one CTA per (document, row); the row is staged in shared
-// memory, the column walk is coalesced across threads.  The reference does this with an n^3
-// boolean broadcast (134 MB at n = 512) or 262 144 Python iterations per document.
+// Pure compare-and-count (integer work).  The reference does this with an n^3 boolean broadcast
+// (134 MB at n = 512) or 262 144 Python iterations per document.
+//
+// Global mode, documents of up to 2048 sentences: #{k : x[k] < x[j]} along a line (row or column) is the
+// lower bound of x[j] in the sorted line, so each warp sorts one line in registers (bitonic network,
+// 32 * NPL values, element g = lane * NPL + r: the short-distance stages are register swaps, only the
+// long-distance ones shuffle), parks the sorted line in shared memory and binary-searches it once per
+// element: O(n^2 log^2 n) per document instead of O(n^3).  Rows are read and written coalesced by their
+// warp; columns go through a shared-memory panel of 32 (8 for n > 512) adjacent columns that the CTA loads
+// and adds back row-segment by row-segment, so every global access uses whole sectors.
+// Local mode and longer documents: one CTA per (document, row) counting kernel.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ss_common.cuh"
 
@@ -49,6 +58,165 @@ __global__ void __launch_bounds__(256) c99_rank_kernel(const float* __restrict__
   }
 }
 
+// ---- global mode by sorting -------------------------------------------------------------------------------
+constexpr int kRankWarps = 8;
+constexpr int kRankThreads = kRankWarps * 32;
+constexpr int kRankSortMaxRows = 2048;
+
+__device__ __forceinline__ int sorted_slot(int g) { return g + (g >> 5); }  // lane-major stores without bank conflicts
+
+// Ascending bitonic sort of 32 * NPL values held as v[r] of every lane, sort index g = lane * NPL + r.
+template <int NPL>
+__device__ __forceinline__ void warp_sort_asc(float (&v)[NPL], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * NPL; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= NPL) {
+        const int lane_mask = j / NPL;
+        // ascending block when bit k of g is clear; k > j >= NPL, so that bit is a lane bit (k = 32 * NPL: always clear)
+        const bool up = ((lane * NPL) & k) == 0;
+        const bool keep_min = up == ((lane & lane_mask) == 0);
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          const float o = __shfl_xor_sync(0xffffffffu, v[r], lane_mask);
+          v[r] = keep_min ? fminf(v[r], o) : fmaxf(v[r], o);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          const int pr = r ^ j;
+          if (pr > r) {
+            const bool up = (((lane * NPL) + r) & k) == 0;
+            const float lo = fminf(v[r], v[pr]), hi = fmaxf(v[r], v[pr]);
+            v[r] = up ? lo : hi;
+            v[pr] = up ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Strict ranks of one line: src[e * stride] for e < n (global or shared memory) -> dst[e * stride] = #{k : src[k] < src[e]}.
+// dst may alias src (the column panel is ranked in place).  `sorted`: 33 * NPL floats of warp-private shared memory.
+template <int NPL>
+__device__ __forceinline__ void rank_line(const float* src, float* dst, int n, float* sorted, int lane) {
+  float v[NPL];
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) {
+    const int e = r * 32 + lane;
+    v[r] = e < n ? src[e] : INFINITY;
+  }
+  warp_sort_asc<NPL>(v, lane);
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) sorted[sorted_slot(lane * NPL + r)] = v[r];
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) {
+    const int e = r * 32 + lane;
+    v[r] = e < n ? src[e] : INFINITY;  // re-read (cache / shared memory) instead of holding a second register copy
+  }
+  __syncwarp();                        // every lane has its values before an in-place dst is written
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) {
+    const int e = r * 32 + lane;
+    if (e < n) {
+      int pos = 0;
+#pragma unroll
+      for (int step = 16 * NPL; step > 0; step >>= 1)
+        if (sorted[sorted_slot(pos + step - 1)] < v[r]) pos += step;
+      dst[e] = static_cast<float>(pos);
+    }
+  }
+  __syncwarp();  // `sorted` is reused by the warp's next line
+}
+
+template <int MAXNPL>
+__device__ __forceinline__ void rank_line_any(const float* src, float* dst, int n, float* sorted, int lane) {
+  if (n <= 32) return rank_line<1>(src, dst, n, sorted, lane);
+  if (n <= 64) return rank_line<2>(src, dst, n, sorted, lane);
+  if (n <= 128) return rank_line<4>(src, dst, n, sorted, lane);
+  if constexpr (MAXNPL >= 16) {
+    if (n <= 256) return rank_line<8>(src, dst, n, sorted, lane);
+    if (n <= 512) return rank_line<16>(src, dst, n, sorted, lane);
+  }
+  if constexpr (MAXNPL >= 64) {
+    if (n <= 1024) return rank_line<32>(src, dst, n, sorted, lane);
+    return rank_line<64>(src, dst, n, sorted, lane);
+  }
+}
+
+// R[i][j] = #{k : S[i][k] < S[i][j]}: one warp per row of the concatenated batch.
+template <int MAXNPL>
+__global__ void __launch_bounds__(kRankThreads) c99_rank_rows_kernel(const float* __restrict__ S_all, const int* __restrict__ offsets,
+                                                                     const long long* __restrict__ s_offsets,
+                                                                     const int* __restrict__ row_doc, int total_rows,
+                                                                     float* __restrict__ R_all) {
+  extern __shared__ float rank_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grow = blockIdx.x * kRankWarps + warp;
+  if (grow >= total_rows) return;
+  const int doc = row_doc[grow];
+  const int base = offsets[doc];
+  const int n = offsets[doc + 1] - base;
+  const size_t line = static_cast<size_t>(s_offsets[doc]) + static_cast<size_t>(grow - base) * n;
+  rank_line_any<MAXNPL>(S_all + line, R_all + line, n, rank_smem + warp * (33 * MAXNPL), lane);
+}
+
+// R[i][j] += #{k : S[k][j] < S[i][j]}: one CTA per PW adjacent columns of the concatenated batch (split at document ends).
+template <int MAXNPL, int PW>
+__global__ void __launch_bounds__(kRankThreads) c99_rank_cols_kernel(const float* __restrict__ S_all, const int* __restrict__ offsets,
+                                                                     const long long* __restrict__ s_offsets,
+                                                                     const int* __restrict__ row_doc, int total_rows,
+                                                                     float* __restrict__ R_all) {
+  extern __shared__ float rank_smem[];
+  float* panel = rank_smem;                                       // [PW][n | 1]
+  float* sorted = rank_smem + PW * (32 * MAXNPL + 1) + (threadIdx.x >> 5) * (33 * MAXNPL);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int g = blockIdx.x * PW;
+  const int end = min(total_rows, g + PW);
+  while (g < end) {
+    const int doc = row_doc[g];
+    const int base = offsets[doc];
+    const int n = offsets[doc + 1] - base;
+    const int j0 = g - base;
+    const int w = min(end, base + n) - g;
+    const int ldp = n | 1;
+    const float* S = S_all + s_offsets[doc];
+    float* R = R_all + s_offsets[doc];
+    for (int idx = threadIdx.x; idx < n * w; idx += kRankThreads) {
+      const int k = idx / w, c = idx - k * w;
+      panel[c * ldp + k] = S[static_cast<size_t>(k) * n + j0 + c];
+    }
+    __syncthreads();
+    for (int c = warp; c < w; c += kRankWarps) rank_line_any<MAXNPL>(panel + c * ldp, panel + c * ldp, n, sorted, lane);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n * w; idx += kRankThreads) {
+      const int k = idx / w, c = idx - k * w;
+      R[static_cast<size_t>(k) * n + j0 + c] += panel[c * ldp + k];
+    }
+    __syncthreads();
+    g += w;
+  }
+}
+
+template <int MAXNPL, int PW>
+static int launch_rank_sorted(const float* S, const int32_t* offsets, const long long* s_offsets, const int* row_doc, int total_rows,
+                              float* R, cudaStream_t st) {
+  const size_t smem_rows = static_cast<size_t>(kRankWarps) * 33 * MAXNPL * sizeof(float);
+  const size_t smem_cols = smem_rows + static_cast<size_t>(PW) * (32 * MAXNPL + 1) * sizeof(float);
+  if (smem_rows > 48 * 1024)
+    SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_rows_kernel<MAXNPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
+  if (smem_cols > 48 * 1024)
+    SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_cols_kernel<MAXNPL, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cols)));
+  c99_rank_rows_kernel<MAXNPL><<<(total_rows + kRankWarps - 1) / kRankWarps, kRankThreads, smem_rows, st>>>(S, offsets, s_offsets, row_doc, total_rows, R);
+  SS_CUDA_CHECK(cudaGetLastError());
+  c99_rank_cols_kernel<MAXNPL, PW><<<(total_rows + PW - 1) / PW, kRankThreads, smem_cols, st>>>(S, offsets, s_offsets, row_doc, total_rows, R);
+  SS_CUDA_CHECK(cudaGetLastError());
+  return SS_OK;
+}
+
 __global__ void c99_row_doc_kernel(const int* __restrict__ offsets, int n_docs, int* __restrict__ row_doc) {
   const int doc = blockIdx.x;
   if (doc >= n_docs) return;
@@ -69,6 +237,12 @@ extern "C" int ss_c99_rank_matrix(const float* S, const int32_t* offsets, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   c99_row_doc_kernel<<<n_docs, 128, 0, st>>>(offsets, n_docs, workspace_rows);
   SS_CUDA_CHECK(cudaGetLastError());
+  if (!use_local_rank && max_doc_rows <= kRankSortMaxRows && !getenv("SS_C99_RANK_COUNTING")) {
+    const long long* so = reinterpret_cast<const long long*>(s_offsets);
+    if (max_doc_rows <= 128) return launch_rank_sorted<4, 32>(S, offsets, so, workspace_rows, total_rows, out_R, st);
+    if (max_doc_rows <= 512) return launch_rank_sorted<16, 32>(S, offsets, so, workspace_rows, total_rows, out_R, st);
+    return launch_rank_sorted<64, 8>(S, offsets, so, workspace_rows, total_rows, out_R, st);
+  }
   if (smem > 48 * 1024)
     SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int m = std::max(3, mask_size | 1);

@@ -177,6 +177,56 @@ def c99_rank_matrix(S: torch.Tensor, plan: RaggedPlan, use_local_rank: bool = Fa
     return R
 
 
+C99_CUTS_MAX_ROWS = 2048  # longest document the device cut search takes (ss_c99_divisive_cuts)
+
+
+def c99_divisive_cuts(R: torch.Tensor, plan: RaggedPlan, min_chunk, max_cuts=None, min_gain: float = 0.01,
+                      stop_by_gain: bool = True, want_profile: bool = False):
+    """Greedy C99 cut search on every document's rank matrix (Method/Semantic_Splitter_Optimized.py:194-238).
+
+    ``min_chunk`` / ``max_cuts``: one int for all documents or a per-document sequence (``max_cuts`` ``None`` or
+    negative = unlimited).  Returns ``(cuts int32 [rows], n_cuts int32 [D], profile float64 [rows] | None)``:
+    document ``d``'s cuts, in pick order, are ``cuts[offsets[d] : offsets[d] + n_cuts[d]]`` and its density
+    profile ``profile[offsets[d] : offsets[d] + n_cuts[d] + 1]``."""
+    dev = _require_cuda(R)
+    if R.dtype != torch.float32 or not R.is_contiguous() or R.numel() < plan.total_s:
+        raise ValueError("R must be the packed float32 output of c99_rank_matrix")
+    if plan.max_rows > C99_CUTS_MAX_ROWS:
+        raise ValueError(f"the device cut search takes documents of at most {C99_CUTS_MAX_ROWS} sentences")
+
+    def per_doc(value, name, default):
+        if value is None:
+            return None, default
+        if np.ndim(value) == 0:
+            return None, int(value)
+        arr = np.ascontiguousarray(value, dtype=np.int32)
+        if arr.shape != (plan.n_docs,):
+            raise ValueError(f"{name} must be a scalar or one value per document")
+        return torch.from_numpy(arr).to(dev), default
+
+    mc_d, mc_all = per_doc(min_chunk, "min_chunk", 0)
+    if (mc_d is None and mc_all < 1) or (mc_d is not None and int(mc_d.min()) < 1):
+        raise ValueError("min_chunk must be >= 1")
+    mx_d, mx_all = per_doc(max_cuts, "max_cuts", -1)
+    sizes = plan.sizes().astype(np.int64)
+    sat_off = np.zeros(plan.n_docs + 1, dtype=np.int64)
+    sat_off[1:] = np.cumsum((sizes + 1) ** 2)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        sat = torch.empty(int(sat_off[-1]), dtype=torch.float64, device=dev)
+        sat_off_d = torch.from_numpy(sat_off[:-1].copy()).to(dev)
+        cuts = torch.zeros(max(plan.total_rows, 1), dtype=torch.int32, device=dev)
+        n_cuts = torch.empty(plan.n_docs, dtype=torch.int32, device=dev)
+        profile = torch.zeros(max(plan.total_rows, 1), dtype=torch.float64, device=dev) if want_profile else None
+        st = lib.ss_c99_divisive_cuts(R.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), sat_off_d.data_ptr(),
+                                      plan.n_docs, max(plan.max_rows, 1), mc_d.data_ptr() if mc_d is not None else None, mc_all,
+                                      mx_d.data_ptr() if mx_d is not None else None, mx_all, float(min_gain), int(bool(stop_by_gain)),
+                                      sat.data_ptr(), cuts.data_ptr(), n_cuts.data_ptr(),
+                                      profile.data_ptr() if profile is not None else None, _stream_ptr(dev))
+        _lib.check(st, "ss_c99_divisive_cuts")
+    return cuts, n_cuts, profile
+
+
 def adjacent_cosine(E: torch.Tensor) -> torch.Tensor:
     """``adj[r] = cos(E[r], E[r+1])`` for the whole concatenated matrix
     (Method/Semantic_Splitter_Optimized.py:140-152,412); the last row gets 0."""

@@ -1,0 +1,157 @@
+"""K10 (ss_c99_divisive_cuts): the C99 divisive cut search on the GPU against
+
+* the reference's own ``_c99_boundaries`` outputs (tests/golden/c99_cuts.npz: boundaries, pick order, density profile),
+* the oracle's literal restatement of Splitter:194-264 (fp32 block means) on seeded batches,
+* the float64 summed-area host statement the kernel mirrors operation for operation (bit-exact, long documents).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import splitter_oracle as spo
+
+pytestmark = pytest.mark.gpu
+
+
+def _topic_rows(rng, n, d, spt, noise=0.6):
+    cent = rng.standard_normal((n // spt + 1, d)).astype(np.float32)
+    E = cent[np.arange(n) // spt] + noise * rng.standard_normal((n, d)).astype(np.float32)
+    return (E / np.linalg.norm(E, axis=1, keepdims=True)).astype(np.float32)
+
+
+def _device_rank(docs, local=False, mask=11):
+    from semanticsearch_b200 import ragged
+    plan = ragged.make_plan([e.shape[0] for e in docs], "cuda")
+    E = torch.from_numpy(np.concatenate(docs, axis=0)).cuda()
+    S = ragged.segmented_simmatrix(E, plan)
+    return plan, ragged.c99_rank_matrix(S, plan, use_local_rank=local, mask_size=mask)
+
+
+def _doc_block(R, plan, d):
+    n = int(plan.offsets[d + 1] - plan.offsets[d])
+    return R[int(plan.s_offsets[d]):int(plan.s_offsets[d + 1])].reshape(n, n)
+
+
+def _assert_same_picks_up_to_near_ties(got, want, R, name):
+    """Pick order must equal the reference's except where two candidate cuts have (exactly computed) gains within
+    fp32 rounding of each other: the reference compares fp32 ndarray.mean() values, the kernel exact float64 sums."""
+    from semanticsearch_b200.Method import Semantic_Splitter_Optimized as SP
+    assert sorted(got) == sorted(want), name
+    if got == want:
+        return
+    blocks = SP._BlockSums(R)
+
+    def gain(bnds, c):
+        a = max(x for x in bnds if x < c)
+        b = min(x for x in bnds if x > c)
+        whole = blocks.mean(a, b)
+        return 0.5 * (blocks.mean(a, c) + blocks.mean(c, b)) - whole
+
+    bnds = [0, R.shape[0]]
+    for x, y in zip(got, want):
+        if x != y:
+            gx, gy = gain(bnds, x), gain(bnds, y)
+            assert abs(gx - gy) <= 2e-6 * max(1.0, abs(gx)), (name, x, y, gx, gy)
+            break
+        bnds.append(x)
+
+
+def test_device_cuts_reproduce_reference_outputs(golden_dir):
+    from semanticsearch_b200 import ragged
+    from semanticsearch_b200.Method import Semantic_Splitter_Optimized as SP
+    g = np.load(os.path.join(golden_dir, "c99_cuts.npz"))
+    meta = json.loads(str(g["meta_json"]))
+    for name, m in meta.items():
+        kw = dict(m["kwargs"])
+        En = g[f"{name}_En"]
+        assert SP._c99_boundaries(En, **kw) == m["bounds"], name
+        # raw kernel: pick order and density profile
+        plan, R = _device_rank([En], bool(kw.get("use_local_rank", False)), int(kw.get("mask_size", 11)))
+        if f"{name}_R" in g.files:
+            if kw.get("use_local_rank", False):
+                # local ranks hinge on the last bits of S (BLAS vs device): search the reference's own rank matrix
+                R = torch.from_numpy(np.ascontiguousarray(g[f"{name}_R"]).ravel()).cuda()
+            else:
+                np.testing.assert_array_equal(R.cpu().numpy().reshape(En.shape[0], -1), g[f"{name}_R"])
+        mode = kw.get("stopping", "gain")
+        cuts, n_cuts, prof = ragged.c99_divisive_cuts(R, plan, kw["min_chunk_size"], kw.get("max_cuts"), kw.get("min_gain", 0.01),
+                                                      stop_by_gain=(mode == "gain"), want_profile=True)
+        cnt = int(n_cuts.cpu()[0])
+        picked = [int(x) for x in cuts.cpu().numpy()[:cnt]]
+        _assert_same_picks_up_to_near_ties(picked, m["cuts"], R.cpu().numpy().reshape(En.shape[0], -1), name)
+        if len(g[f"{name}_D"]) and picked == m["cuts"]:
+            # the reference sums fp32 blocks, the kernel an exact float64 table
+            np.testing.assert_allclose(prof.cpu().numpy()[:cnt + 1], g[f"{name}_D"], rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("mode,local", [("gain", False), ("profile", False), ("gain", True)])
+def test_batch_matches_oracle(mode, local):
+    from semanticsearch_b200.Method import Semantic_Splitter_Optimized as SP
+    rng = np.random.default_rng(20 + len(mode) + int(local))
+    sizes = [2, 5, 6, 7, 11, 23, 40, 64, 65, 97, 128, 129, 180, 33, 8] if not local else [6, 17, 40, 64, 90]
+    docs = [_topic_rows(rng, n, 32, int(rng.integers(4, 14))) for n in sizes]
+    mins = [int(rng.integers(1, 7)) for _ in sizes]
+    got = SP.c99_boundaries_batch(docs, mins, None, 0.01, use_local_rank=local, mask_size=9, stopping=mode, knee_c=1.0, smooth_window=3)
+    for d, E in enumerate(docs):
+        # rank matrix from the device (its similarity differs from BLAS in the last bits; the rank kernel has its own
+        # exact test), so this check isolates the search
+        _plan, Rd = _device_rank([E], local, 9)
+        want, _picked, _series = spo.c99_divisive_ref(Rd.cpu().numpy().reshape(sizes[d], sizes[d]), mins[d], None, 0.01, mode, 1.0, 3)
+        assert got[d] == want, (d, sizes[d], mins[d])
+
+
+@pytest.mark.parametrize("n,m", [(520, 6), (700, 9), (1500, 20), (2048, 30)])
+def test_long_documents_bit_exact_against_float64_statement(n, m):
+    """Documents past 512 sentences (4 and 8 candidate positions per thread): cuts, pick order and profile
+    equal the float64 summed-area host statement exactly."""
+    from semanticsearch_b200 import ragged
+    from semanticsearch_b200.Method import Semantic_Splitter_Optimized as SP
+    rng = np.random.default_rng(n)
+    docs = [_topic_rows(rng, n, 48, 25), _topic_rows(rng, 77, 48, 9)]
+    plan, R = _device_rank(docs)
+    Rh = R.cpu().numpy()
+    for mode in ("gain", "profile"):
+        cuts, n_cuts, prof = ragged.c99_divisive_cuts(R, plan, [m, 4], None, 0.01, stop_by_gain=(mode == "gain"), want_profile=True)
+        cuts_h, n_h, prof_h = cuts.cpu().numpy(), n_cuts.cpu().numpy(), prof.cpu().numpy()
+        for d, mm in enumerate((m, 4)):
+            Rd = _doc_block(Rh, plan, d)
+            blocks = SP._BlockSums(Rd)
+            base, cnt = int(plan.offsets[d]), int(n_h[d])
+            picked = [int(x) for x in cuts_h[base:base + cnt]]
+            want = SP._divisive_cuts(Rd, mm, None, 0.01, mode, 1.2, 3)
+            got = sorted(set(picked)) if mode == "gain" else SP._profile_knee(picked, prof_h[base:base + cnt + 1], 1.2, 3)
+            assert got == want and cnt > 0
+            # profile: exact replay of the host's ascending-segment sum
+            bnds = [0, Rd.shape[0]]
+            for i, c in enumerate(picked, start=1):
+                bnds = sorted(bnds + [c])
+                tot, area = 0.0, 0
+                for a, b in zip(bnds[:-1], bnds[1:]):
+                    tot += blocks.total(a, b)
+                    area += (b - a) * (b - a)
+                assert prof_h[base + i] == tot / float(area)
+
+
+def test_edge_cases_and_limits():
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(5)
+    docs = [_topic_rows(rng, n, 16, 4) for n in (2, 5, 6, 30, 30)]
+    plan, R = _device_rank(docs)
+    # per-document min_chunk and max_cuts: too short (n < 2m), exactly 2m, capped at 1 and 0 cuts
+    cuts, n_cuts, prof = ragged.c99_divisive_cuts(R, plan, [3, 3, 3, 3, 3], [-1, -1, -1, 1, 0], 0.0, stop_by_gain=False)
+    n_h = n_cuts.cpu().numpy().tolist()
+    assert prof is None and n_h[0] == 0 and n_h[1] == 0 and n_h[2] == 1 and n_h[3] == 1 and n_h[4] == 0
+    assert int(cuts.cpu()[int(plan.offsets[2])]) == 3  # the only admissible cut of a 6-sentence document
+    # without the gain test the search exhausts every admissible cut: all segments end shorter than 2m
+    cuts, n_cuts, _ = ragged.c99_divisive_cuts(R, plan, 3, None, 0.01, stop_by_gain=False)
+    b = sorted([0, 30] + cuts.cpu().numpy()[int(plan.offsets[3]):int(plan.offsets[3]) + int(n_cuts.cpu()[3])].tolist())
+    assert all(3 <= y - x < 6 for x, y in zip(b[:-1], b[1:]))
+    with pytest.raises(ValueError):
+        ragged.c99_divisive_cuts(R, plan, 0)
+    with pytest.raises(ValueError):
+        ragged.c99_divisive_cuts(R, plan, [3, 3])
+    with pytest.raises(RuntimeError):
+        ragged.c99_divisive_cuts(R.cpu(), plan, 3)

@@ -92,11 +92,22 @@ def test_grouping_dropin_reproduces_reference_chunks(golden_dir, fake_text_stack
                     assert mine[key] == pytest.approx(ref[key], abs=2e-4)
 
 
+def _strict_rank_by_sorting(S):
+    """#{k: S[i,k] < S[i,j]} + #{k: S[k,j] < S[i,j]} via searchsorted (cheap at large n; checked against the oracle below)."""
+    row = np.stack([np.searchsorted(np.sort(r), r, side="left") for r in S])
+    col = np.stack([np.searchsorted(np.sort(c), c, side="left") for c in S.T]).T
+    return (row + col).astype(np.float32)
+
+
 def test_c99_rank_kernel_exact_on_own_similarity():
     from semanticsearch_b200 import ragged
     rng = np.random.default_rng(9)
-    sizes = [12, 40, 97, 130]
+    sizes = [12, 40, 97, 130, 33, 2, 300, 257, 512, 64]
     rows = [rng.standard_normal((n, 32)).astype(np.float32) for n in sizes]
+    rows[2][5] = rows[2][60]          # duplicated sentences: exact ties inside rows and columns
+    rows[2][61] = rows[2][60]
+    rows[6][100:110] = rows[6][0]
+    rows[3][7] = 0.0                  # a zero embedding: a row / column of zeros
     plan = ragged.make_plan(sizes, "cuda")
     E = torch.from_numpy(np.concatenate(rows)).cuda()
     S = ragged.segmented_simmatrix(E, plan)
@@ -106,8 +117,25 @@ def test_c99_rank_kernel_exact_on_own_similarity():
     for d, n in enumerate(sizes):
         blk = slice(plan.s_offsets[d], plan.s_offsets[d + 1])
         Sd = S_h[blk].reshape(n, n)
-        np.testing.assert_array_equal(Rg[blk].reshape(n, n), spo.c99_global_rank_ref(Sd))
-        np.testing.assert_array_equal(Rl[blk].reshape(n, n), spo.c99_local_rank_ref(Sd, 11))
+        want = spo.c99_global_rank_ref(Sd)
+        np.testing.assert_array_equal(_strict_rank_by_sorting(Sd), want)
+        np.testing.assert_array_equal(Rg[blk].reshape(n, n), want)
+        if n <= 130:
+            np.testing.assert_array_equal(Rl[blk].reshape(n, n), spo.c99_local_rank_ref(Sd, 11))
+
+
+@pytest.mark.parametrize("sizes", [[100, 90, 128, 5], [1100, 40, 513], [2048, 7], [2300, 64]])
+def test_c99_global_rank_all_size_classes(sizes):
+    """Every kernel variant (<= 128, <= 512, <= 2048 sentences: sorting; longer: counting) on non-symmetric input."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(sum(sizes))
+    plan = ragged.make_plan(sizes, "cuda")
+    blocks = [np.round(rng.standard_normal((n, n)), 2).astype(np.float32) for n in sizes]  # rounded: many ties, not symmetric
+    S = torch.from_numpy(np.concatenate([b.ravel() for b in blocks])).cuda()
+    R = ragged.c99_rank_matrix(S, plan, use_local_rank=False).cpu().numpy()
+    for d, n in enumerate(sizes):
+        got = R[plan.s_offsets[d]:plan.s_offsets[d + 1]].reshape(n, n)
+        np.testing.assert_array_equal(got, _strict_rank_by_sorting(blocks[d]))
 
 
 def test_splitter_dropin_reproduces_reference_groups(golden_dir, fake_text_stack):

@@ -117,6 +117,26 @@ def test_splitter_pass_matches_reference(golden_dir):
             np.testing.assert_array_equal(R, g[f"{name}_c99_R"])
 
 
+def test_c99_divisive_search_matches_reference(golden_dir):
+    """The reference's own _c99_boundaries outputs (boundaries, pick order, density profile) for 14 cases."""
+    g = _load(golden_dir, "c99_cuts.npz")
+    meta = json.loads(str(g["meta_json"]))
+    assert len(meta) >= 14
+    for name, m in meta.items():
+        kw = dict(m["kwargs"])
+        S = spo.c99_similarity_ref(g[f"{name}_En"])
+        if kw.pop("use_local_rank", False):
+            R = spo.c99_local_rank_ref(S, kw.pop("mask_size", 11))
+        else:
+            R = spo.c99_global_rank_ref(S)
+        if f"{name}_R" in g.files:
+            np.testing.assert_array_equal(R, g[f"{name}_R"])
+        bounds, picked, series = spo.c99_divisive_ref(R, **kw)
+        assert bounds == m["bounds"], name
+        assert picked == m["cuts"], name
+        np.testing.assert_array_equal(np.asarray(series, dtype=np.float64), g[f"{name}_D"])
+
+
 def test_p95_breakpoints_known_answer():
     adj = np.array([0.9, 0.8, 0.1, 0.85, 0.95, 0.2, 0.7, 0.75, 0.6, 0.65, 0.3], dtype=float)
     thr, bp = spo.p95_breakpoints_ref(adj)
