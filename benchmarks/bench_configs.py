@@ -267,7 +267,7 @@ def config7(args):
     cuts, n_cuts, _ = ragged.c99_divisive_cuts(R, plan, mins)
     peak, src = hbm_peak()
     sat = int(((sizes.astype(np.int64) + 1) ** 2).sum())
-    alg_cut = 4 * plan.total_s + 2 * 8 * sat  # read R, write the float64 table once per pass (two passes)
+    alg_cut = 4 * plan.total_s + 8 * sat  # read R once, write the float64 table once
     from oracle import splitter_oracle as spo
     sample = list(range(0, D, max(1, D // 6)))[:6]
     Eh = [E[plan.offsets[d]:plan.offsets[d + 1]].cpu().numpy() for d in sample]

@@ -8,10 +8,11 @@
 // max(min_gain, 0.1 * |mean of the segment|) or no candidate is left.
 //
 // One CTA per document:
-//   1. a float64 summed-area table P of R is built in global memory (L2-resident, 2 MB at n = 512) with the
-//      summation order of np.cumsum(np.cumsum(R, axis=0), axis=1): sequential down the columns (coalesced),
-//      then sequential along the rows through 32 x 32 shared-memory tiles (coalesced loads/stores, one row per
-//      lane).  For the default global rank matrix every entry is an integer < 2^11, so every block sum is exact.
+//   1. a float64 summed-area table P of R is built in global memory (2 MB at n = 512) in ONE sweep over 32 x 32
+//      tiles along anti-diagonals, with the summation order of np.cumsum(np.cumsum(R, axis=0), axis=1): inside a
+//      tile one lane per column runs down the rows, then one lane per row runs along the columns; column and row
+//      carries pass between tiles through shared memory, one barrier per diagonal.  R is read once, P written
+//      once.  For the default global rank matrix every entry is an integer < 2^11, so every block sum is exact.
 //   2. each thread owns candidate positions c; it keeps its segment [a, b), the segment's position in the
 //      reference's segment list and the gain of cutting at c in registers.  A split only invalidates the gains
 //      of the positions inside the split segment; everything else is reused, so a round is one block arg-max
@@ -28,9 +29,9 @@ namespace ss {
 
 constexpr int kCutThreads = 256;
 constexpr int kCutWarps = kCutThreads / 32;
-constexpr int kCutTileLd = 33;
-constexpr int kCutTile = 32 * kCutTileLd;                                   // doubles per warp
-constexpr size_t kCutSmemBytes = static_cast<size_t>(kCutWarps) * kCutTile * 8;  // 67 584 B, reused by the search
+constexpr int kCutTile = 32 * 32;  // doubles per warp
+// tiles (64 KB, reused by the search) + column and row carries of the table sweep
+constexpr size_t cut_smem_bytes(int cpt) { return static_cast<size_t>(kCutWarps) * kCutTile * 8 + 2 * static_cast<size_t>(cpt) * kCutThreads * 8; }
 constexpr int kCutMaxRows = 2048;
 
 struct CutParams {
@@ -61,8 +62,8 @@ __device__ __forceinline__ double sat_mean(const double* P, int ld, int a, int b
 
 // (gain desc, list position asc, cut asc): true when x is better than y.
 struct CutBest {
-  double gain;
-  int idx, c, a, b;
+  double gain, whole;  // whole = mean of the candidate's segment (the stop rule needs the winner's)
+  int idx, c;
 };
 __device__ __forceinline__ bool cut_better(const CutBest& x, const CutBest& y) {
   if (x.gain != y.gain) return x.gain > y.gain;
@@ -72,18 +73,17 @@ __device__ __forceinline__ bool cut_better(const CutBest& x, const CutBest& y) {
 __device__ __forceinline__ CutBest cut_shfl_down(const CutBest& v, int d) {
   CutBest o;
   o.gain = __shfl_down_sync(0xffffffffu, v.gain, d);
+  o.whole = __shfl_down_sync(0xffffffffu, v.whole, d);
   o.idx = __shfl_down_sync(0xffffffffu, v.idx, d);
   o.c = __shfl_down_sync(0xffffffffu, v.c, d);
-  o.a = __shfl_down_sync(0xffffffffu, v.a, d);
-  o.b = __shfl_down_sync(0xffffffffu, v.b, d);
   return o;
 }
 
 template <int CPT>
-__global__ void __launch_bounds__(kCutThreads) c99_divisive_kernel(const CutParams p) {
+__global__ void __launch_bounds__(kCutThreads, CPT == 2 ? 3 : 1) c99_divisive_kernel(const CutParams p) {
   extern __shared__ __align__(16) unsigned char cut_smem[];
   __shared__ CutBest w_best[kCutWarps];
-  __shared__ int dec[5];  // stop, list position, cut, a, b
+  __shared__ int dec[3];  // stop, list position, cut
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int doc = blockIdx.x;
   const int row_base = p.offsets[doc];
@@ -103,53 +103,78 @@ __global__ void __launch_bounds__(kCutThreads) c99_divisive_kernel(const CutPara
   const int ld = n + 1;
 
   // ---- summed-area table: P[i+1][j+1] = sum R[0..i][0..j] ------------------------------------------------
+  // One sweep over 32 x 32 tiles along anti-diagonals: tile (b, jc) continues column sums from tile (b-1, jc) and row
+  // sums from tile (b, jc-1), both finished one diagonal earlier, so R is read once and P written once while every
+  // addition happens in np.cumsum(np.cumsum(R, 0), 1) order.  The warp's next tile of R is prefetched into registers.
   for (int t = tid; t <= n; t += kCutThreads) {
     P[t] = 0.0;
     P[static_cast<size_t>(t) * ld] = 0.0;
   }
-  for (int j = tid; j < n; j += kCutThreads) {  // np.cumsum(axis=0): sequential down column j
-    double acc = 0.0;
-    int i = 0;
-    for (; i + 8 <= n; i += 8) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = R[static_cast<size_t>(i + u) * n + j];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        acc = __dadd_rn(acc, static_cast<double>(v[u]));
-        P[static_cast<size_t>(i + u + 1) * ld + j + 1] = acc;
-      }
-    }
-    for (; i < n; ++i) {
-      acc = __dadd_rn(acc, static_cast<double>(R[static_cast<size_t>(i) * n + j]));
-      P[static_cast<size_t>(i + 1) * ld + j + 1] = acc;
-    }
-  }
-  __syncthreads();
   {
-    double* tile = reinterpret_cast<double*>(cut_smem) + warp * kCutTile;
-    for (int g = warp; g * 32 < n; g += kCutWarps) {  // np.cumsum(axis=1): sequential along each row, 32 rows per warp
-      const int row0 = g * 32;
+    const int T = (n + 31) >> 5;
+    double* tile = reinterpret_cast<double*>(cut_smem) + warp * kCutTile;  // [32][32], column index XOR row (conflict-free both ways)
+    double* colcarry = reinterpret_cast<double*>(cut_smem) + kCutWarps * kCutTile;
+    double* rowcarry = colcarry + CPT * kCutThreads;
+    float v[32], vn[32];
+    auto load_tile = [&](float (&dst)[32], int tb, int tjc) {
+      const int row0 = tb * 32, col = tjc * 32 + lane;
       const int rows = min(32, n - row0);
-      double carry = 0.0;
-      for (int jc = 0; jc < n; jc += 32) {
-        const int cols = min(32, n - jc);
-        if (lane < cols)
-          for (int r = 0; r < rows; ++r) tile[r * kCutTileLd + lane] = P[static_cast<size_t>(row0 + r + 1) * ld + jc + lane + 1];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) dst[r] = (r < rows && col < n) ? R[static_cast<size_t>(row0 + r) * n + col] : 0.f;
+    };
+    bool have = false;
+    for (int d = 0; d < 2 * T - 1; ++d) {
+      const int b_lo = max(0, d - T + 1);
+      const int cnt = min(d, T - 1) - b_lo + 1;
+      for (int t = warp; t < cnt; t += kCutWarps) {
+        const int tb = b_lo + t, tjc = d - tb;
+        if (!have) load_tile(v, tb, tjc);
+        int nb, njc;
+        bool nvalid;
+        if (t + kCutWarps < cnt) {
+          nb = tb + kCutWarps;
+          njc = d - nb;
+          nvalid = true;
+        } else {
+          const int d2 = d + 1;
+          const int b_lo2 = max(0, d2 - T + 1);
+          nvalid = d2 < 2 * T - 1 && warp < min(d2, T - 1) - b_lo2 + 1;
+          nb = b_lo2 + warp;
+          njc = d2 - nb;
+        }
+        if (nvalid) load_tile(vn, nb, njc);
+        const int row0 = tb * 32, col0 = tjc * 32;
+        const int rows = min(32, n - row0), cols = min(32, n - col0);
+        if (lane < cols) {  // np.cumsum(axis=0): lane = column, sequential down the rows
+          double cc = tb ? colcarry[col0 + lane] : 0.0;
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            if (r < rows) {
+              cc = __dadd_rn(cc, static_cast<double>(v[r]));
+              tile[r * 32 + (lane ^ r)] = cc;
+            }
+          colcarry[col0 + lane] = cc;
+        }
         __syncwarp();
-        if (lane < rows)
+        if (lane < rows) {  // np.cumsum(axis=1): lane = row, sequential along the columns
+          double rc = tjc ? rowcarry[row0 + lane] : 0.0;
           for (int c = 0; c < cols; ++c) {
-            carry = __dadd_rn(carry, tile[lane * kCutTileLd + c]);
-            tile[lane * kCutTileLd + c] = carry;
+            rc = __dadd_rn(rc, tile[lane * 32 + (c ^ lane)]);
+            tile[lane * 32 + (c ^ lane)] = rc;
           }
+          rowcarry[row0 + lane] = rc;
+        }
         __syncwarp();
         if (lane < cols)
-          for (int r = 0; r < rows; ++r) P[static_cast<size_t>(row0 + r + 1) * ld + jc + lane + 1] = tile[r * kCutTileLd + lane];
+          for (int r = 0; r < rows; ++r) P[static_cast<size_t>(row0 + r + 1) * ld + col0 + lane + 1] = tile[r * 32 + (lane ^ r)];
         __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = vn[r];
+        have = nvalid;
       }
+      __syncthreads();  // the carries of this diagonal are visible to the next one
     }
   }
-  __syncthreads();
 
   // ---- divisive search -------------------------------------------------------------------------------------
   int* bnd[2] = {reinterpret_cast<int*>(cut_smem), reinterpret_cast<int*>(cut_smem) + (kCutMaxRows + 8)};  // sorted boundaries
@@ -162,7 +187,7 @@ __global__ void __launch_bounds__(kCutThreads) c99_divisive_kernel(const CutPara
     if (want_profile) p.out_profile[row_base] = __ddiv_rn(__dadd_rn(0.0, sat_total(P, ld, 0, n)), static_cast<double>(static_cast<long long>(n) * n));
   }
   int seg_a[CPT], seg_b[CPT], seg_idx[CPT];
-  double gain[CPT];
+  double gain[CPT], whole_of[CPT];
   unsigned alive = 0u, dirty = 0u;
 #pragma unroll
   for (int r = 0; r < CPT; ++r) {
@@ -171,6 +196,7 @@ __global__ void __launch_bounds__(kCutThreads) c99_divisive_kernel(const CutPara
     seg_b[r] = n;
     seg_idx[r] = 0;
     gain[r] = -INFINITY;
+    whole_of[r] = 0.0;
     if (c > 0 && c < n) {
       alive |= 1u << r;
       dirty |= 1u << r;
@@ -182,7 +208,7 @@ __global__ void __launch_bounds__(kCutThreads) c99_divisive_kernel(const CutPara
     best.gain = -INFINITY;
     best.idx = 0x7fffffff;
     best.c = 0x7fffffff;
-    best.a = best.b = 0;
+    best.whole = 0.0;
 #pragma unroll
     for (int r = 0; r < CPT; ++r) {
       if (!((alive >> r) & 1u)) continue;
@@ -193,15 +219,15 @@ __global__ void __launch_bounds__(kCutThreads) c99_divisive_kernel(const CutPara
         if (b - a >= 2 * m && c >= a + m && c <= b - m) {  // :210-214
           const double whole = sat_mean(P, ld, a, b);
           g = __dsub_rn(__dmul_rn(0.5, __dadd_rn(sat_mean(P, ld, a, c), sat_mean(P, ld, c, b))), whole);  // :219
+          whole_of[r] = whole;
         }
         gain[r] = g;
       }
       CutBest mine;
       mine.gain = gain[r];
+      mine.whole = whole_of[r];
       mine.idx = seg_idx[r];
       mine.c = c;
-      mine.a = a;
-      mine.b = b;
       if (mine.gain > -INFINITY && cut_better(mine, best)) best = mine;
     }
     dirty = 0u;
@@ -226,14 +252,12 @@ __global__ void __launch_bounds__(kCutThreads) c99_divisive_kernel(const CutPara
       if (lane == 0) {
         bool stop = !(best.gain > -INFINITY) || (max_cuts >= 0 && n_cuts >= max_cuts);  // :225
         if (!stop && p.by_gain) {
-          const double floor_gain = fmax(p.min_gain, __dmul_rn(0.1, fabs(sat_mean(P, ld, best.a, best.b))));  // :224
+          const double floor_gain = fmax(p.min_gain, __dmul_rn(0.1, fabs(best.whole)));  // :224
           stop = best.gain < floor_gain;                                                                      // :228
         }
         dec[0] = stop ? 1 : 0;
         dec[1] = best.idx;
         dec[2] = best.c;
-        dec[3] = best.a;
-        dec[4] = best.b;
         if (!stop) p.out_cuts[row_base + n_cuts] = best.c;
       }
     }
@@ -322,13 +346,13 @@ extern "C" int ss_c99_divisive_cuts(const float* R, const int32_t* offsets, cons
   p.out_n_cuts = out_n_cuts;
   p.out_profile = out_profile;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  auto launch = [&](auto kernel) -> int {
-    SS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCutSmemBytes)));
-    kernel<<<n_docs, kCutThreads, kCutSmemBytes, st>>>(p);
+  auto launch = [&](auto kernel, size_t smem) -> int {
+    SS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kernel<<<n_docs, kCutThreads, smem, st>>>(p);
     SS_CUDA_CHECK(cudaGetLastError());
     return SS_OK;
   };
-  if (max_doc_rows <= 2 * kCutThreads) return launch(c99_divisive_kernel<2>);
-  if (max_doc_rows <= 4 * kCutThreads) return launch(c99_divisive_kernel<4>);
-  return launch(c99_divisive_kernel<8>);
+  if (max_doc_rows <= 2 * kCutThreads) return launch(c99_divisive_kernel<2>, cut_smem_bytes(2));
+  if (max_doc_rows <= 4 * kCutThreads) return launch(c99_divisive_kernel<4>, cut_smem_bytes(4));
+  return launch(c99_divisive_kernel<8>, cut_smem_bytes(8));
 }

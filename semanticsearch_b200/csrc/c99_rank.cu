@@ -10,9 +10,9 @@
 // lower bound of x[j] in the sorted line, so each warp sorts one line in registers (bitonic network,
 // 32 * NPL values, element g = lane * NPL + r: the short-distance stages are register swaps, only the
 // long-distance ones shuffle), parks the sorted line in shared memory and binary-searches it once per
-// element: O(n^2 log^2 n) per document instead of O(n^3).  Rows are read and written coalesced by their
-// warp; columns go through a shared-memory panel of 32 (8 for n > 512) adjacent columns that the CTA loads
-// and adds back row-segment by row-segment, so every global access uses whole sectors.
+// element: O(n^2 log^2 n) per document instead of O(n^3).  Columns go first, through a shared-memory panel of
+// 32 (8 for n > 512) adjacent columns that the CTA fills with cp.async and stores back row-segment by
+// row-segment (whole sectors); rows follow, each warp adding its ranks to R with coalesced accesses.
 // Local mode and longer documents: one CTA per (document, row) counting kernel.
 #include <algorithm>
 #include <cstdlib>
@@ -98,15 +98,24 @@ __device__ __forceinline__ void warp_sort_asc(float (&v)[NPL], int lane) {
   }
 }
 
-// Strict ranks of one line: src[e * stride] for e < n (global or shared memory) -> dst[e * stride] = #{k : src[k] < src[e]}.
-// dst may alias src (the column panel is ranked in place).  `sorted`: 33 * NPL floats of warp-private shared memory.
-template <int NPL>
+// Strict ranks of one line: src[e] for e < n (global or shared memory) -> dst[e] = #{k : src[k] < src[e]} (+ the previous
+// dst[e] when ACC).  dst may alias src (the column panel is ranked in place).  `sorted`: 33 * NPL floats of warp-private
+// shared memory.
+template <int NPL, bool ACC>
 __device__ __forceinline__ void rank_line(const float* src, float* dst, int n, float* sorted, int lane) {
   float v[NPL];
 #pragma unroll
   for (int r = 0; r < NPL; ++r) {
     const int e = r * 32 + lane;
     v[r] = e < n ? src[e] : INFINITY;
+  }
+  float prev[ACC ? NPL : 1];
+  if constexpr (ACC) {  // issued now, consumed after the sort
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+      const int e = r * 32 + lane;
+      prev[r] = e < n ? dst[e] : 0.f;
+    }
   }
   warp_sort_asc<NPL>(v, lane);
 #pragma unroll
@@ -126,28 +135,29 @@ __device__ __forceinline__ void rank_line(const float* src, float* dst, int n, f
 #pragma unroll
       for (int step = 16 * NPL; step > 0; step >>= 1)
         if (sorted[sorted_slot(pos + step - 1)] < v[r]) pos += step;
-      dst[e] = static_cast<float>(pos);
+      if constexpr (ACC) dst[e] = static_cast<float>(pos) + prev[r];
+      else dst[e] = static_cast<float>(pos);
     }
   }
   __syncwarp();  // `sorted` is reused by the warp's next line
 }
 
-template <int MAXNPL>
+template <int MAXNPL, bool ACC>
 __device__ __forceinline__ void rank_line_any(const float* src, float* dst, int n, float* sorted, int lane) {
-  if (n <= 32) return rank_line<1>(src, dst, n, sorted, lane);
-  if (n <= 64) return rank_line<2>(src, dst, n, sorted, lane);
-  if (n <= 128) return rank_line<4>(src, dst, n, sorted, lane);
+  if (n <= 32) return rank_line<1, ACC>(src, dst, n, sorted, lane);
+  if (n <= 64) return rank_line<2, ACC>(src, dst, n, sorted, lane);
+  if (n <= 128) return rank_line<4, ACC>(src, dst, n, sorted, lane);
   if constexpr (MAXNPL >= 16) {
-    if (n <= 256) return rank_line<8>(src, dst, n, sorted, lane);
-    if (n <= 512) return rank_line<16>(src, dst, n, sorted, lane);
+    if (n <= 256) return rank_line<8, ACC>(src, dst, n, sorted, lane);
+    if (n <= 512) return rank_line<16, ACC>(src, dst, n, sorted, lane);
   }
   if constexpr (MAXNPL >= 64) {
-    if (n <= 1024) return rank_line<32>(src, dst, n, sorted, lane);
-    return rank_line<64>(src, dst, n, sorted, lane);
+    if (n <= 1024) return rank_line<32, ACC>(src, dst, n, sorted, lane);
+    return rank_line<64, ACC>(src, dst, n, sorted, lane);
   }
 }
 
-// R[i][j] = #{k : S[i][k] < S[i][j]}: one warp per row of the concatenated batch.
+// R[i][j] += #{k : S[i][k] < S[i][j]} (second pass: coalesced read-modify-write): one warp per row of the concatenated batch.
 template <int MAXNPL>
 __global__ void __launch_bounds__(kRankThreads) c99_rank_rows_kernel(const float* __restrict__ S_all, const int* __restrict__ offsets,
                                                                      const long long* __restrict__ s_offsets,
@@ -161,10 +171,12 @@ __global__ void __launch_bounds__(kRankThreads) c99_rank_rows_kernel(const float
   const int base = offsets[doc];
   const int n = offsets[doc + 1] - base;
   const size_t line = static_cast<size_t>(s_offsets[doc]) + static_cast<size_t>(grow - base) * n;
-  rank_line_any<MAXNPL>(S_all + line, R_all + line, n, rank_smem + warp * (33 * MAXNPL), lane);
+  rank_line_any<MAXNPL, true>(S_all + line, R_all + line, n, rank_smem + warp * (33 * MAXNPL), lane);
 }
 
-// R[i][j] += #{k : S[k][j] < S[i][j]}: one CTA per PW adjacent columns of the concatenated batch (split at document ends).
+// R[i][j] = #{k : S[k][j] < S[i][j]} (first pass: plain stores): one CTA per PW adjacent columns of the concatenated
+// batch (split at document ends).  The panel is filled with 4-byte cp.async copies — every thread has its whole share
+// in flight at once — and written back without reading R.
 template <int MAXNPL, int PW>
 __global__ void __launch_bounds__(kRankThreads) c99_rank_cols_kernel(const float* __restrict__ S_all, const int* __restrict__ offsets,
                                                                      const long long* __restrict__ s_offsets,
@@ -185,16 +197,33 @@ __global__ void __launch_bounds__(kRankThreads) c99_rank_cols_kernel(const float
     const int ldp = n | 1;
     const float* S = S_all + s_offsets[doc];
     float* R = R_all + s_offsets[doc];
-    for (int idx = threadIdx.x; idx < n * w; idx += kRankThreads) {
-      const int k = idx / w, c = idx - k * w;
-      panel[c * ldp + k] = S[static_cast<size_t>(k) * n + j0 + c];
+    if (w == PW) {
+      for (int idx = threadIdx.x; idx < n * PW; idx += kRankThreads) {
+        const int k = idx / PW, c = idx % PW;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(panel + c * ldp + k)), "l"(S + static_cast<size_t>(k) * n + j0 + c) : "memory");
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < n * w; idx += kRankThreads) {
+        const int k = idx / w, c = idx - k * w;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(panel + c * ldp + k)), "l"(S + static_cast<size_t>(k) * n + j0 + c) : "memory");
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    for (int c = warp; c < w; c += kRankWarps) rank_line_any<MAXNPL>(panel + c * ldp, panel + c * ldp, n, sorted, lane);
+    for (int c = warp; c < w; c += kRankWarps) rank_line_any<MAXNPL, false>(panel + c * ldp, panel + c * ldp, n, sorted, lane);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < n * w; idx += kRankThreads) {
-      const int k = idx / w, c = idx - k * w;
-      R[static_cast<size_t>(k) * n + j0 + c] += panel[c * ldp + k];
+    if (w == PW) {
+#pragma unroll 4
+      for (int idx = threadIdx.x; idx < n * PW; idx += kRankThreads) {
+        const int k = idx / PW, c = idx % PW;
+        R[static_cast<size_t>(k) * n + j0 + c] = panel[c * ldp + k];
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < n * w; idx += kRankThreads) {
+        const int k = idx / w, c = idx - k * w;
+        R[static_cast<size_t>(k) * n + j0 + c] = panel[c * ldp + k];
+      }
     }
     __syncthreads();
     g += w;
@@ -210,9 +239,9 @@ static int launch_rank_sorted(const float* S, const int32_t* offsets, const long
     SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_rows_kernel<MAXNPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
   if (smem_cols > 48 * 1024)
     SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_cols_kernel<MAXNPL, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cols)));
-  c99_rank_rows_kernel<MAXNPL><<<(total_rows + kRankWarps - 1) / kRankWarps, kRankThreads, smem_rows, st>>>(S, offsets, s_offsets, row_doc, total_rows, R);
-  SS_CUDA_CHECK(cudaGetLastError());
   c99_rank_cols_kernel<MAXNPL, PW><<<(total_rows + PW - 1) / PW, kRankThreads, smem_cols, st>>>(S, offsets, s_offsets, row_doc, total_rows, R);
+  SS_CUDA_CHECK(cudaGetLastError());
+  c99_rank_rows_kernel<MAXNPL><<<(total_rows + kRankWarps - 1) / kRankWarps, kRankThreads, smem_rows, st>>>(S, offsets, s_offsets, row_doc, total_rows, R);
   SS_CUDA_CHECK(cudaGetLastError());
   return SS_OK;
 }
