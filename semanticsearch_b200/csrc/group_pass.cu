@@ -66,21 +66,26 @@ __device__ __forceinline__ double np_lerp(double a, double b, double g) {
 constexpr int kFastMaxN = 512;  // fast path: a whole row lives in 4..16 registers per lane
 constexpr int kListCap = 2048;  // candidates per quantile the shared-memory selection can hold
 
-// One warp sorts a[0..64) (shared memory) in descending order.
-__device__ __forceinline__ void warp_bitonic64_desc(uint64_t* a, int lane) {
-#pragma unroll 1
-  for (int k2 = 2; k2 <= 64; k2 <<= 1) {
-#pragma unroll 1
-    for (int j = k2 >> 1; j > 0; j >>= 1) {
-      const int i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1));
-      const int q = i | j;
-      const uint64_t x = a[i], y = a[q];
-      const bool desc = (i & k2) == 0;
-      if (desc ? (x < y) : (x > y)) {
-        a[i] = y;
-        a[q] = x;
+// Descending bitonic sort of 64 keys held two per lane (sort index g = 2 * lane + r): the distance-1 stages are a
+// register swap, the others one shuffle per key.  After the call key g of the sorted order is k[g & 1] of lane g >> 1.
+template <typename K>
+__device__ __forceinline__ void warp_sort64_desc(K& k0, K& k1, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 64; k <<= 1) {
+    const bool desc_blk = ((lane * 2) & k) == 0;  // k = 64: always (the whole sequence ends descending)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 2) {
+        const int lane_mask = j >> 1;
+        const bool keep_max = desc_blk == ((lane & lane_mask) == 0);
+        const K o0 = __shfl_xor_sync(0xffffffffu, k0, lane_mask), o1 = __shfl_xor_sync(0xffffffffu, k1, lane_mask);
+        k0 = keep_max ? max(k0, o0) : min(k0, o0);
+        k1 = keep_max ? max(k1, o1) : min(k1, o1);
+      } else {
+        const K hi = max(k0, k1), lo = min(k0, k1);
+        k0 = desc_blk ? hi : lo;
+        k1 = desc_blk ? lo : hi;
       }
-      __syncwarp();
     }
   }
 }
@@ -173,7 +178,13 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
       uint32_t o[NREG];  // order-preserving bits of the sharpened value; 0 = column past the end
       double rs = 0.0;
 #pragma unroll
+      for (int j = 0; j < NREG; ++j) {  // the whole row in flight before any of it is consumed
+        const int c = lane + 32 * j;
+        o[j] = (32 * j < n && c < n) ? __float_as_uint(srow[c]) : 0u;
+      }
+#pragma unroll
       for (int j = 0; j < NREG; ++j) {
+        const float s_raw = __uint_as_float(o[j]);
         o[j] = 0u;
         if (32 * j < n) {
           const int c = lane + 32 * j;
@@ -183,7 +194,7 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
             // sigmoid(((S - mu) / sigma) / tau) with one FMA, ex2.approx and rcp.approx: a few ulp from
             // the reference's fp32 expression (Grouping:105-106), far inside the 1e-5 bound; saturates
             // to exactly 0 / 1 like numpy's exp overflow does
-            float v = __frcp_rn(1.0f + exp2f(-((srow[c] - mu) * zscale)));
+            float v = __frcp_rn(1.0f + exp2f(-((s_raw - mu) * zscale)));
             if (c == r) v = 0.f;
             orow[c] = v;
             rs += static_cast<double>(v);
@@ -217,13 +228,8 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
         m2 = max(m2, min(m1, o[j]));
         m1 = max(m1, o[j]);
       }
-      uint32_t L = 0x80000000u;  // every real column has bit 31 set
-#pragma unroll 1
-      for (int bit = 30; bit >= 0; --bit) {
-        const uint32_t cand = L | (1u << bit);
-        const int c = __reduce_add_sync(0xffffffffu, (m1 >= cand ? 1 : 0) + (m2 >= cand ? 1 : 0));
-        if (c >= width) L = cand;
-      }
+      warp_sort64_desc<uint32_t>(m1, m2, lane);  // width <= n real columns are in the sample, so L is a real value
+      const uint32_t L = __shfl_sync(0xffffffffu, ((width - 1) & 1) ? m2 : m1, (width - 1) >> 1);
       int c_ge = 0;
 #pragma unroll
       for (int j = 0; j < NREG; ++j) c_ge += (o[j] >= L) ? 1 : 0;
@@ -274,14 +280,19 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
         }
       }
       __syncwarp();
-      warp_bitonic64_desc(scr, lane);
+      unsigned long long k0 = scr[2 * lane], k1 = scr[2 * lane + 1];
+      warp_sort64_desc<unsigned long long>(k0, k1, lane);
       int* oi = cx.knn_idx + static_cast<size_t>(row_base + r) * kKnnWidth;
       float* ov = cx.knn_val + static_cast<size_t>(row_base + r) * kKnnWidth;
-      for (int s = lane; s < kKnnWidth; s += 32) {
-        const uint64_t key = scr[s];
-        const bool ok = s < width;
-        oi[s] = ok ? static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull)) : -1;
-        ov[s] = ok ? ordered_to_float(static_cast<uint32_t>(key >> 32)) : 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // lane holds sorted slots 2 * lane and 2 * lane + 1
+        const int s = 2 * lane + h;
+        const unsigned long long key = h ? k1 : k0;
+        if (s < kKnnWidth) {
+          const bool ok = s < width;
+          oi[s] = ok ? static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull)) : -1;
+          ov[s] = ok ? ordered_to_float(static_cast<uint32_t>(key >> 32)) : 0.f;
+        }
       }
       __syncwarp();
     }
