@@ -194,22 +194,25 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
             // sigmoid(((S - mu) / sigma) / tau) with one FMA, ex2.approx and rcp.approx: a few ulp from
             // the reference's fp32 expression (Grouping:105-106), far inside the 1e-5 bound; saturates
             // to exactly 0 / 1 like numpy's exp overflow does
-            float v = __frcp_rn(1.0f + exp2f(-((s_raw - mu) * zscale)));
+            float e, v;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-((s_raw - mu) * zscale)));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(1.0f + e));
             if (c == r) v = 0.f;
             orow[c] = v;
-            rs += static_cast<double>(v);
-            o[j] = float_to_ordered(v);
+            const double vd = static_cast<double>(v);  // float64 sums: 0.1 * std(vals) stays within 1e-9 of numpy's
+            rs += vd;                                   // zeros add nothing: also the sum of the positive values
+            pos_s2 = fma(vd, vd, pos_s2);
+            o[j] = __float_as_uint(v) | 0x80000000u;    // float_to_ordered of a non-negative value
             if (v > 0.f) {
               pos = true;
               bits = __float_as_uint(v);
-              pos_s1 += static_cast<double>(v);
-              pos_s2 += static_cast<double>(v) * static_cast<double>(v);
               ++pos_cnt;
             }
           }
           hist_add_aggregated(cx.hist, lin_bin(__uint_as_float(bits)), pos, lane);
         }
       }
+      pos_s1 += rs;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
       if (lane == 0) {
