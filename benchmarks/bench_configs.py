@@ -53,14 +53,19 @@ def hbm_peak():
         return 6650.0, "fallback"
 
 
-def cuda_time(fn, steps, warmup=3):
+def cuda_time(fn, steps, warmup=3, after=None):
+    """Mean CUDA-event time of `fn` on the current stream; `after` (optional) joins side streams before the stop event."""
     for _ in range(warmup):
         fn()
+    if after:
+        after()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         fn()
+    if after:
+        after()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / steps

@@ -227,7 +227,7 @@ def c99_divisive_cuts(R: torch.Tensor, plan: RaggedPlan, min_chunk, max_cuts=Non
     return cuts, n_cuts, profile
 
 
-def adjacent_cosine(E: torch.Tensor) -> torch.Tensor:
+def adjacent_cosine(E: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``adj[r] = cos(E[r], E[r+1])`` for the whole concatenated matrix
     (Method/Semantic_Splitter_Optimized.py:140-152,412); the last row gets 0."""
     dev = _require_cuda(E)
@@ -235,28 +235,37 @@ def adjacent_cosine(E: torch.Tensor) -> torch.Tensor:
         raise ValueError("E must be a contiguous 2-D tensor")
     lib = _lib.load()
     with torch.cuda.device(dev):
-        out = torch.empty(E.shape[0], dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty(E.shape[0], dtype=torch.float32, device=dev)
+        elif out.dtype != torch.float32 or out.numel() != E.shape[0] or not out.is_cuda or not out.is_contiguous():
+            raise ValueError("out must be a contiguous CUDA float32 tensor with one element per row of E")
         st = lib.ss_segmented_adjacent_cosine(E.data_ptr(), E.shape[0], E.shape[1], _dtype_code(E), out.data_ptr(),
                                               _stream_ptr(dev))
         _lib.check(st, "ss_segmented_adjacent_cosine")
     return out
 
 
-def segmented_percentile(adj: torch.Tensor, plan: RaggedPlan, pct: float = 95.0, want_stats: bool = True):
+def segmented_percentile(adj: torch.Tensor, plan: RaggedPlan, pct: float = 95.0, want_stats: bool = True, out=None):
     """Per-document percentile threshold of ``1 - adj`` + breakpoint flags (BASELINE.json cfg 3)
     and, optionally, the splitter's robust statistics (Splitter:340-356,417-437).
     Returns ``(thr [D] f64, flags [rows] u8, stats [D,4] f64 | None, smooth [rows] f32 | None)``;
     stats columns are (median, MAD+1e-9, P25, P75) of the median-of-3 smoothed series.
-    ``adj`` is updated in place: the slot of each document's last sentence is set to 0."""
+    ``adj`` is updated in place: the slot of each document's last sentence is set to 0.
+    ``out``: optional ``(thr, flags, stats, smooth)`` tuple of a previous call to overwrite."""
     dev = _require_cuda(adj)
     if adj.dtype != torch.float32 or adj.dim() != 1 or not adj.is_contiguous() or adj.numel() != plan.total_rows:
         raise ValueError("adj must be the float32 [total_rows] output of adjacent_cosine")
     lib = _lib.load()
     with torch.cuda.device(dev):
-        thr = torch.empty(plan.n_docs, dtype=torch.float64, device=dev)
-        flags = torch.empty(plan.total_rows, dtype=torch.uint8, device=dev)
-        stats = torch.empty((plan.n_docs, 4), dtype=torch.float64, device=dev) if want_stats else None
-        smooth = torch.empty(plan.total_rows, dtype=torch.float32, device=dev) if want_stats else None
+        if out is not None:   # (thr, flags, stats, smooth) buffers of a previous call with the same plan shape
+            thr, flags, stats, smooth = out
+            if thr.numel() != plan.n_docs or flags.numel() != plan.total_rows or (want_stats and (stats is None or smooth is None)):
+                raise ValueError("out does not match the plan")
+        else:
+            thr = torch.empty(plan.n_docs, dtype=torch.float64, device=dev)
+            flags = torch.empty(plan.total_rows, dtype=torch.uint8, device=dev)
+            stats = torch.empty((plan.n_docs, 4), dtype=torch.float64, device=dev) if want_stats else None
+            smooth = torch.empty(plan.total_rows, dtype=torch.float32, device=dev) if want_stats else None
         st = lib.ss_segmented_percentile(adj.data_ptr(), plan.offsets_d.data_ptr(), plan.n_docs, max(plan.max_rows, 1),
                                          float(pct), thr.data_ptr(), flags.data_ptr(),
                                          stats.data_ptr() if want_stats else None,
