@@ -172,6 +172,7 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
   const float mu = cx.mu;
   const float zscale = 1.4426950408889634f / (cx.sigma * cx.tau);  // log2(e) / (sigma * tau)
   uint64_t* scr = cx.scr;
+  unsigned int c_lo = 0u, c_hi = 0u;  // this warp's counts of bins 0 and 2047, flushed once
     for (int r = warp; r < n; r += kGrpWarps) {
       const float* srow = S + static_cast<size_t>(r) * n;
       float* orow = sharp + static_cast<size_t>(r) * n;
@@ -209,7 +210,13 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
               ++pos_cnt;
             }
           }
-          hist_add_aggregated(cx.hist, lin_bin(__uint_as_float(bits)), pos, lane);
+          // histogram: the saturated ends of the sigmoid (bins 0 and 2047 hold a quarter of the values and more)
+          // are counted with ballots into warp-uniform registers; every other bin takes a plain shared-memory atomic
+          const unsigned int bin = lin_bin(__uint_as_float(bits));
+          const bool sat_lo = pos && bin == 0u, sat_hi = pos && bin == 2047u;
+          c_lo += __popc(__ballot_sync(0xffffffffu, sat_lo));
+          c_hi += __popc(__ballot_sync(0xffffffffu, sat_hi));
+          if (pos && !sat_lo && !sat_hi) atomicAdd(&cx.hist[bin], 1u);
         }
       }
       pos_s1 += rs;
@@ -299,6 +306,10 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
       }
       __syncwarp();
     }
+  if (lane == 0) {
+    if (c_lo) atomicAdd(&cx.hist[0], c_lo);
+    if (c_hi) atomicAdd(&cx.hist[2047], c_hi);
+  }
 }
 
 

@@ -247,3 +247,25 @@ def test_group_pass_crowded_bin_takes_radix_fallback():
         rows_d = slice(plan.offsets[d], plan.offsets[d + 1])
         np.testing.assert_array_equal(kidx[rows_d, :w], idx_ref)   # ties -> ascending column index
         np.testing.assert_array_equal(kval[rows_d, :w], val_ref)
+
+
+def test_splitter_passes_accept_output_buffers():
+    """adjacent_cosine / segmented_percentile into caller-owned buffers give the same bits as fresh allocations."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(41)
+    sizes = [2, 9, 33, 130, 1, 64]
+    E = torch.from_numpy(np.concatenate(topic_docs(rng, sizes, 48))).cuda()
+    plan = ragged.make_plan(sizes, "cuda")
+    adj0 = ragged.adjacent_cosine(E)
+    ref = ragged.segmented_percentile(adj0.clone(), plan, 95.0, want_stats=True)
+    adj1 = torch.full_like(adj0, 7.0)
+    assert ragged.adjacent_cosine(E, out=adj1) is adj1
+    bufs = tuple(torch.full_like(t, 3) for t in ref)
+    got = ragged.segmented_percentile(adj1, plan, 95.0, want_stats=True, out=bufs)
+    for a, b, c in zip(got, ref, bufs):
+        assert a is c
+        assert torch.equal(torch.nan_to_num(a.double(), nan=-1.0), torch.nan_to_num(b.double(), nan=-1.0))
+    with pytest.raises(ValueError):
+        ragged.adjacent_cosine(E, out=torch.empty(3, device="cuda"))
+    with pytest.raises(ValueError):
+        ragged.segmented_percentile(adj1, plan, 95.0, out=(bufs[0][:1], bufs[1], bufs[2], bufs[3]))
