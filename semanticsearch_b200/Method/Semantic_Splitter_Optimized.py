@@ -144,7 +144,7 @@ def c99_boundaries_batch(doc_embeddings: Sequence[np.ndarray], min_chunk_sizes, 
         plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
         E = torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
         S = ragged.segmented_simmatrix(E, plan)
-        R = ragged.c99_rank_matrix(S, plan, use_local_rank=bool(use_local_rank), mask_size=int(mask_size))
+        R = ragged.c99_rank_matrix(S, plan, use_local_rank=bool(use_local_rank), mask_size=int(mask_size), symmetric=True)
         del S
         cuts, n_cuts, profile = ragged.c99_divisive_cuts(R, plan, [mins[d] for d in ids], max_cuts, float(min_gain),
                                                          stop_by_gain=(mode == "gain"), want_profile=(mode == "profile"))

@@ -158,7 +158,7 @@ __device__ __forceinline__ void rank_line_any(const float* src, float* dst, int 
 }
 
 // R[i][j] += #{k : S[i][k] < S[i][j]} (second pass: coalesced read-modify-write): one warp per row of the concatenated batch.
-template <int MAXNPL>
+template <int MAXNPL, bool ACC>
 __global__ void __launch_bounds__(kRankThreads) c99_rank_rows_kernel(const float* __restrict__ S_all, const int* __restrict__ offsets,
                                                                      const long long* __restrict__ s_offsets,
                                                                      const int* __restrict__ row_doc, int total_rows,
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kRankThreads) c99_rank_rows_kernel(const float
   const int base = offsets[doc];
   const int n = offsets[doc + 1] - base;
   const size_t line = static_cast<size_t>(s_offsets[doc]) + static_cast<size_t>(grow - base) * n;
-  rank_line_any<MAXNPL, true>(S_all + line, R_all + line, n, rank_smem + warp * (33 * MAXNPL), lane);
+  rank_line_any<MAXNPL, ACC>(S_all + line, R_all + line, n, rank_smem + warp * (33 * MAXNPL), lane);
 }
 
 // R[i][j] = #{k : S[k][j] < S[i][j]} (first pass: plain stores): one CTA per PW adjacent columns of the concatenated
@@ -230,18 +230,63 @@ __global__ void __launch_bounds__(kRankThreads) c99_rank_cols_kernel(const float
   }
 }
 
+// Symmetric S: #{k : S[k][j] < S[i][j]} = #{k : S[j][k] < S[j][i]}, i.e. the column ranks are the transposed row ranks.
+// R holds the row ranks; CTA (doc, I) adds the transposed tile to every tile pair (I, J >= I) in place through shared
+// memory (both directions coalesced).
+__global__ void __launch_bounds__(256) c99_rank_symmetrize_kernel(const int* __restrict__ offsets, const long long* __restrict__ s_offsets,
+                                                                  float* __restrict__ R_all) {
+  __shared__ float ta[32][33], tb[32][33];
+  const int doc = blockIdx.x, I = blockIdx.y;
+  const int n = offsets[doc + 1] - offsets[doc];
+  const int T = (n + 31) >> 5;
+  if (I >= T) return;
+  float* R = R_all + s_offsets[doc];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 row groups of 4 rows
+  for (int J = I; J < T; ++J) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = ty * 4 + q;
+      const int ia = I * 32 + r, ja = J * 32 + tx;  // tile (I, J)
+      const int ib = J * 32 + r, jb = I * 32 + tx;  // tile (J, I)
+      ta[r][tx] = (ia < n && ja < n) ? R[static_cast<size_t>(ia) * n + ja] : 0.f;
+      tb[r][tx] = (ib < n && jb < n) ? R[static_cast<size_t>(ib) * n + jb] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = ty * 4 + q;
+      const int ia = I * 32 + r, ja = J * 32 + tx;
+      const int ib = J * 32 + r, jb = I * 32 + tx;
+      if (ia < n && ja < n) R[static_cast<size_t>(ia) * n + ja] = ta[r][tx] + tb[tx][r];
+      if (J != I && ib < n && jb < n) R[static_cast<size_t>(ib) * n + jb] = tb[r][tx] + ta[tx][r];
+    }
+    __syncthreads();
+  }
+}
+
 template <int MAXNPL, int PW>
-static int launch_rank_sorted(const float* S, const int32_t* offsets, const long long* s_offsets, const int* row_doc, int total_rows,
-                              float* R, cudaStream_t st) {
+static int launch_rank_sorted(const float* S, const int32_t* offsets, const long long* s_offsets, const int* row_doc, int n_docs,
+                              int total_rows, int max_doc_rows, bool symmetric, float* R, cudaStream_t st) {
   const size_t smem_rows = static_cast<size_t>(kRankWarps) * 33 * MAXNPL * sizeof(float);
   const size_t smem_cols = smem_rows + static_cast<size_t>(PW) * (32 * MAXNPL + 1) * sizeof(float);
+  const int row_blocks = (total_rows + kRankWarps - 1) / kRankWarps;
+  if (symmetric) {
+    if (smem_rows > 48 * 1024)
+      SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_rows_kernel<MAXNPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
+    c99_rank_rows_kernel<MAXNPL, false><<<row_blocks, kRankThreads, smem_rows, st>>>(S, offsets, s_offsets, row_doc, total_rows, R);
+    SS_CUDA_CHECK(cudaGetLastError());
+    const dim3 grid(static_cast<unsigned>(n_docs), static_cast<unsigned>((max_doc_rows + 31) / 32));
+    c99_rank_symmetrize_kernel<<<grid, 256, 0, st>>>(offsets, s_offsets, R);
+    SS_CUDA_CHECK(cudaGetLastError());
+    return SS_OK;
+  }
   if (smem_rows > 48 * 1024)
-    SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_rows_kernel<MAXNPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
+    SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_rows_kernel<MAXNPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
   if (smem_cols > 48 * 1024)
     SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_cols_kernel<MAXNPL, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cols)));
   c99_rank_cols_kernel<MAXNPL, PW><<<(total_rows + PW - 1) / PW, kRankThreads, smem_cols, st>>>(S, offsets, s_offsets, row_doc, total_rows, R);
   SS_CUDA_CHECK(cudaGetLastError());
-  c99_rank_rows_kernel<MAXNPL><<<(total_rows + kRankWarps - 1) / kRankWarps, kRankThreads, smem_rows, st>>>(S, offsets, s_offsets, row_doc, total_rows, R);
+  c99_rank_rows_kernel<MAXNPL, true><<<row_blocks, kRankThreads, smem_rows, st>>>(S, offsets, s_offsets, row_doc, total_rows, R);
   SS_CUDA_CHECK(cudaGetLastError());
   return SS_OK;
 }
@@ -266,11 +311,13 @@ extern "C" int ss_c99_rank_matrix(const float* S, const int32_t* offsets, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   c99_row_doc_kernel<<<n_docs, 128, 0, st>>>(offsets, n_docs, workspace_rows);
   SS_CUDA_CHECK(cudaGetLastError());
+  const bool symmetric = (use_local_rank & 2) != 0;  // bit 1: the caller guarantees S == S^T bit for bit (output of K3)
+  use_local_rank &= 1;
   if (!use_local_rank && max_doc_rows <= kRankSortMaxRows && !getenv("SS_C99_RANK_COUNTING")) {
     const long long* so = reinterpret_cast<const long long*>(s_offsets);
-    if (max_doc_rows <= 128) return launch_rank_sorted<4, 32>(S, offsets, so, workspace_rows, total_rows, out_R, st);
-    if (max_doc_rows <= 512) return launch_rank_sorted<16, 32>(S, offsets, so, workspace_rows, total_rows, out_R, st);
-    return launch_rank_sorted<64, 8>(S, offsets, so, workspace_rows, total_rows, out_R, st);
+    if (max_doc_rows <= 128) return launch_rank_sorted<4, 32>(S, offsets, so, workspace_rows, n_docs, total_rows, max_doc_rows, symmetric, out_R, st);
+    if (max_doc_rows <= 512) return launch_rank_sorted<16, 32>(S, offsets, so, workspace_rows, n_docs, total_rows, max_doc_rows, symmetric, out_R, st);
+    return launch_rank_sorted<64, 8>(S, offsets, so, workspace_rows, n_docs, total_rows, max_doc_rows, symmetric, out_R, st);
   }
   if (smem > 48 * 1024)
     SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -161,8 +161,11 @@ def similarity_distribution(S: torch.Tensor, plan: RaggedPlan, eps: float = 1e-5
     return out
 
 
-def c99_rank_matrix(S: torch.Tensor, plan: RaggedPlan, use_local_rank: bool = False, mask_size: int = 11) -> torch.Tensor:
-    """C99 rank transform of every document's S (Method/Semantic_Splitter_Optimized.py:171-192), packed like S."""
+def c99_rank_matrix(S: torch.Tensor, plan: RaggedPlan, use_local_rank: bool = False, mask_size: int = 11,
+                    symmetric: bool = False) -> torch.Tensor:
+    """C99 rank transform of every document's S (Method/Semantic_Splitter_Optimized.py:171-192), packed like S.
+    ``symmetric=True`` promises ``S == S.T`` bit for bit (the output of ``segmented_simmatrix``): the global mode then
+    takes the column ranks as the transposed row ranks instead of sorting every column."""
     dev = _require_cuda(S)
     if S.dtype != torch.float32 or not S.is_contiguous() or S.numel() < plan.total_s:
         raise ValueError("S must be the packed float32 output of segmented_simmatrix")
@@ -171,7 +174,8 @@ def c99_rank_matrix(S: torch.Tensor, plan: RaggedPlan, use_local_rank: bool = Fa
         R = torch.empty(plan.total_s, dtype=torch.float32, device=dev)
         ws = torch.empty(max(plan.total_rows, 1), dtype=torch.int32, device=dev)
         st = lib.ss_c99_rank_matrix(S.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), plan.n_docs,
-                                    plan.total_rows, max(plan.max_rows, 1), int(bool(use_local_rank)), int(mask_size),
+                                    plan.total_rows, max(plan.max_rows, 1),
+                                    int(bool(use_local_rank)) | (2 if (symmetric and not use_local_rank) else 0), int(mask_size),
                                     ws.data_ptr(), R.data_ptr(), _stream_ptr(dev))
         _lib.check(st, "ss_c99_rank_matrix")
     return R

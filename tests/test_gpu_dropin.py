@@ -122,6 +122,16 @@ def test_c99_rank_kernel_exact_on_own_similarity():
         np.testing.assert_array_equal(Rg[blk].reshape(n, n), want)
         if n <= 130:
             np.testing.assert_array_equal(Rl[blk].reshape(n, n), spo.c99_local_rank_ref(Sd, 11))
+    # both similarity kernels mirror their tiles, so S is symmetric bit for bit and the transposed-row-rank shortcut applies
+    for algo in ("tc", "ffma"):
+        Sa = ragged.segmented_simmatrix(E, plan, algo=algo)
+        Sa_h = Sa.cpu().numpy()
+        Rs = ragged.c99_rank_matrix(Sa, plan, symmetric=True).cpu().numpy()
+        Rn = ragged.c99_rank_matrix(Sa, plan).cpu().numpy()
+        np.testing.assert_array_equal(Rs, Rn)
+        for d, n in enumerate(sizes):
+            Sd = Sa_h[plan.s_offsets[d]:plan.s_offsets[d + 1]].reshape(n, n)
+            np.testing.assert_array_equal(Sd, Sd.T)
 
 
 @pytest.mark.parametrize("sizes", [[100, 90, 128, 5], [1100, 40, 513], [2048, 7], [2300, 64]])
