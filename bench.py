@@ -124,7 +124,7 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # DRAM traffic per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
@@ -406,7 +406,7 @@ def run_ours(args):
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_reference_qps(args)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         if peer is not None:
             peer.close()
@@ -414,8 +414,23 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_JSON_OUT = None  # file object on the process's real stdout; everything else written to fd 1 goes to stderr
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    """The contract is ONE JSON line on stdout: libraries that print there on their own (NCCL writes its version line to
+    stdout at communicator creation) are sent to stderr by pointing fd 1 at fd 2 for the duration of the run."""
+    global _JSON_OUT
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
