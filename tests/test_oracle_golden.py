@@ -160,3 +160,66 @@ def test_oracle_against_live_reference():
         C = rng.standard_normal((300, d)).astype(np.float32)
         q = rng.standard_normal((1, d)).astype(np.float32)
         np.testing.assert_allclose(ro.cosine_similarity_ref(q, C), ref.rank.cosine_similarity(q, C), atol=2e-7, rtol=0)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+def test_c99_oracle_against_live_reference():
+    """Fresh random documents through the reference's own _c99_boundaries (Splitter:155-264), every run with different
+    sizes / chunk floors / stopping rules: boundaries, pick order and density profile must be the reference's."""
+    from oracle.gen_golden import capture_locals, topic_doc
+    ref = ref_shim.load_reference()
+    rng = np.random.default_rng(2024)
+    for trial in range(8):
+        n = int(rng.integers(6, 70))
+        E = topic_doc(rng, n, 24, sent_per_topic=int(rng.integers(3, 10)), noise=0.6)
+        En = (E / np.linalg.norm(E, axis=1, keepdims=True)).astype(np.float32)
+        kw = {"min_chunk_size": int(rng.integers(1, 6)), "stopping": "profile" if trial % 3 == 2 else "gain",
+              "min_gain": float(rng.choice([0.0, 0.01, 2.0])), "use_local_rank": trial % 4 == 3}
+        if trial % 5 == 4:
+            kw["max_cuts"] = int(rng.integers(1, 4))
+        want, grabbed = capture_locals(ref.split._c99_boundaries, ("R", "cuts", "D_series"), {"_c99_boundaries"}, En, **kw)
+        loc = grabbed.get("_c99_boundaries", {})
+        S = spo.c99_similarity_ref(En)
+        R = spo.c99_local_rank_ref(S, 11) if kw["use_local_rank"] else spo.c99_global_rank_ref(S)
+        if "R" in loc:
+            np.testing.assert_array_equal(R, loc["R"])
+        got, picked, series = spo.c99_divisive_ref(R, kw["min_chunk_size"], kw.get("max_cuts"), kw["min_gain"], kw["stopping"])
+        assert got == [int(x) for x in want], (trial, kw)
+        assert picked == [int(x) for x in loc.get("cuts", [])], (trial, kw)
+        np.testing.assert_array_equal(np.asarray(series, dtype=np.float64), np.asarray(loc.get("D_series", []), dtype=np.float64))
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+def test_splitter_and_grouping_oracles_against_live_reference():
+    """Random documents through process_sentence_splitting_with_semantics and semantic_grouping_main: the locals the
+    reference computes on the dense path equal the oracle's restatement bit for bit."""
+    from oracle.gen_golden import capture_locals, topic_doc
+    ref = ref_shim.load_reference()
+    rng = np.random.default_rng(77)
+    for trial in range(3):
+        n = int(rng.integers(12, 60))
+        E = topic_doc(rng, n, 32, sent_per_topic=int(rng.integers(4, 10)), noise=0.6)
+        text, _sents = ref_shim.make_doc(E, tag=f"lv{trial}")
+        _out, grabbed = capture_locals(ref.split.process_sentence_splitting_with_semantics,
+                                       ("embeddings", "adj_sims", "adj_base", "adj_for_valley", "valley_tau"),
+                                       {"process_sentence_splitting_with_semantics"}, text, embedding_model="m",
+                                       device="cpu", silent=True)
+        loc = grabbed["process_sentence_splitting_with_semantics"]
+        np.testing.assert_array_equal(so.normalize_rows_1e9(E), np.asarray(loc["embeddings"]))
+        adj = spo.adjacent_sims_ref(E)
+        np.testing.assert_array_equal(adj, np.asarray(loc["adj_sims"], dtype=np.float64))
+        st = spo.robust_stats_ref(adj, 3)
+        np.testing.assert_array_equal(st["adj_base"], np.asarray(loc["adj_base"], dtype=np.float64))
+        np.testing.assert_array_equal(st["adj_for_valley"], np.asarray(loc["adj_for_valley"], dtype=np.float64))
+        assert st["valley_tau"] == float(loc["valley_tau"])
+        _out, grabbed = capture_locals(ref.group.semantic_grouping_main, ("sim_sharp", "centrality", "eff_edge_floor", "mu", "sigma"),
+                                       {"semantic_grouping_main"}, text, f"doc_lv{trial}", "m", device="cpu", silent=True,
+                                       collect_metadata=True)
+        loc = grabbed.get("semantic_grouping_main", {})
+        if "sim_sharp" not in loc:
+            continue
+        res = go.grouping_pass_ref(so.similarity_matrix_ref(E))
+        np.testing.assert_array_equal(res["sim_sharp"], np.asarray(loc["sim_sharp"]))
+        np.testing.assert_array_equal(res["centrality"], np.asarray(loc["centrality"]))
+        assert res["thresholds"]["edge_floor"] == float(loc["eff_edge_floor"])
+        assert res["mu"] == float(loc["mu"]) and res["sigma"] == float(loc["sigma"])
