@@ -63,3 +63,46 @@ def test_sentinels_without_gpu():
         assert G.semantic_grouping_main("only one sentence here", "d1", "m", silent=True) == [("d1_single", "only one sentence here", None)]
     finally:
         seg.set_sentence_splitter(None)
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_shim", fromlist=["x"]).reference_available(), reason="reference tree not mounted")
+def test_host_stage_matches_live_reference_on_random_documents():
+    """Fresh random documents through the reference's semantic_grouping_main (CPU): the host stage, fed with the oracle's
+    restatement of the device pass and the reference's own kNN graph (its argsort ties are unspecified), must emit the
+    same clusters, method and metadata."""
+    from oracle import ref_shim, simmatrix_oracle as so
+    from oracle.gen_golden import capture_locals, topic_doc
+    ref = ref_shim.load_reference()
+    rng = np.random.default_rng(909)
+    checked = 0
+    for trial in range(6):
+        n = int(rng.integers(8, 70))
+        E = topic_doc(rng, n, 32, sent_per_topic=int(rng.integers(3, 12)), noise=float(rng.choice([0.4, 0.7])))
+        text, sents = ref_shim.make_doc(E, tag=f"hg{trial}")
+        want, grabbed = capture_locals(ref.group.semantic_grouping_main, ("sim_sharp", "W_all", "k_eff_all", "method_used"),
+                                       {"semantic_grouping_main"}, text, f"doc_hg{trial}", "m", device="cpu", silent=True,
+                                       collect_metadata=True)
+        loc = grabbed.get("semantic_grouping_main", {})
+        if "W_all" not in loc:
+            continue
+        S = so.similarity_matrix_ref(E)
+        res = go.grouping_pass_ref(S)
+        np.testing.assert_array_equal(res["sim_sharp"], np.asarray(loc["sim_sharp"]))
+        idx, val = go.knn_lists_ref(res["sim_sharp"], res["k_eff_all"])
+        kidx = np.full((n, 33), -1, np.int32)
+        kval = np.zeros((n, 33), np.float32)
+        kidx[:, :idx.shape[1]] = idx
+        kval[:, :val.shape[1]] = val
+        thr = res["thresholds"]
+        dp = G.DevicePass(sim_matrix=S, sim_sharp=res["sim_sharp"], centrality=res["centrality"], mu=res["mu"], sigma=res["sigma"],
+                          q80=thr["edge_floor"], q65=thr["tau_merge"], q60=thr["global_merge_thr"],
+                          reassign_delta=thr["reassign_delta"], n_positive=thr["count"], k_all=res["k_eff_all"],
+                          knn_idx=kidx, knn_val=kval)
+        merged, method, _W = G.cluster_from_device_pass(dp, W_override=np.asarray(loc["W_all"]))
+        assert method == str(loc["method_used"])
+        chunks = G._emit(f"doc_hg{trial}", text, sents, merged, method, dp, collect_metadata=True)
+        assert [c[0] for c in chunks] == [w[0] for w in want], trial
+        for (cid, _t, mj), (_wid, _wt, wj) in zip(chunks, want):
+            assert json.loads(mj) == json.loads(wj), cid
+        checked += 1
+    assert checked >= 4
