@@ -117,6 +117,14 @@ int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, int dtype,
                         void* workspace, size_t workspace_bytes,
                         uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
 
+/* ss_cosine_topk_gemm for a RESIDENT corpus: with corpus_norms_valid != 0 the head of `workspace` still holds the
+ * inverse row norms an earlier call (valid or not) computed for this same corpus into this same workspace, and the
+ * norm pre-pass over the corpus is skipped.  The caller owns that guarantee (same corpus bytes, same workspace
+ * pointer, no other call used the workspace in between). */
+int ss_cosine_topk_gemm_resident(const void* corpus, int64_t n_rows, int dim, int dtype, const void* queries, int n_queries,
+                                 int k, uint32_t index_base, void* workspace, size_t workspace_bytes, int corpus_norms_valid,
+                                 uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
+
 /* ---- K7: tensor-core streaming cosine + fused top-k, medium query batches -----------------------
  * Same contract as ss_cosine_topk_gemm (bf16/fp16, one dtype for corpus and queries, dim % 8 == 0)
  * with k <= 1024: the corpus tile is the MMA M operand and up to 64 queries stay resident in shared

@@ -31,6 +31,8 @@ _SIGNATURES = {
     "ss_cosine_topk_gemm_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "ss_cosine_topk_gemm": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_uint32, c_void_p, c_size_t,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ss_cosine_topk_gemm_resident": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_uint32, c_void_p, c_size_t,
+                                             c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ss_cosine_topk_tcstream_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "ss_cosine_topk_tcstream": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_uint32, c_void_p, c_size_t,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -122,6 +122,9 @@ class ShardedCorpus:
             merge = merge or similarity.topk_merge
         self._local_search = local_search
         self._merge = merge
+        from . import similarity as _sim
+        # the shard is resident and immutable for the life of this object: K2 may keep its row norms between searches
+        self._resident = _sim.ResidentIndex() if local_search is _sim.cosine_topk else None
 
     @property
     def world_size(self) -> int:
@@ -129,8 +132,9 @@ class ShardedCorpus:
 
     def search(self, queries: torch.Tensor, k: int, algo: str = "auto"):
         """Global top-k for ``queries`` (replicated on every rank): ``(scores, indices)``."""
+        extra = {"resident": self._resident} if self._resident is not None else {}
         scores, idx, keys = self._local_search(self.local_rows, queries, k, index_base=self.row_offset,
-                                               return_keys=True, algo=algo)
+                                               return_keys=True, algo=algo, **extra)
         world = self.world_size
         if world == 1:
             return scores, idx

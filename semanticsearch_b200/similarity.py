@@ -90,14 +90,38 @@ def choose_algo(corpus: torch.Tensor, queries: torch.Tensor, k: int) -> str:
     return "stream"
 
 
+class ResidentIndex:
+    """Token of a corpus that stays resident and unchanged in HBM (``sharded.ShardedCorpus`` owns one).  It carries its
+    own K2 workspace, whose head keeps the corpus's inverse row norms: while buffer and corpus (pointer, shape, dtype) are
+    those of the token's previous K2 call, the next call skips the norm pre-pass (one read of the whole corpus).  No
+    other caller touches this workspace, so a CUDA graph captured from such a call stays valid."""
+
+    __slots__ = ("ws", "state")
+
+    def __init__(self):
+        self.ws = None      # grow-only uint8 workspace of this corpus's K2 calls
+        self.state = None   # (workspace data_ptr, corpus data_ptr, rows, dim, dtype) of the last K2 call
+
+    def workspace(self, dev: torch.device, nbytes: int) -> torch.Tensor:
+        if self.ws is None or self.ws.numel() < nbytes or self.ws.device != dev:
+            self.ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+            self.state = None
+        return self.ws
+
+    def invalidate(self) -> None:
+        """Call after the corpus bytes change."""
+        self.state = None
+
+
 def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_base: int = 0,
-                return_keys: bool = False, algo: str = "auto"):
+                return_keys: bool = False, algo: str = "auto", resident: "ResidentIndex | None" = None):
     """Top-k cosine similarity of each query row against every corpus row.
 
     Device form of ``cosine_similarity(q, C)[0]`` + ``np.argsort(-s)[:k]``
     (Tool/rank_chunks_optimized.py:215-216,225).  Returns ``(scores fp32 [B,k], indices int64
     [B,k])`` best-first, ties resolved to the lower index; with ``return_keys`` also the packed
-    int64 keys used for multi-GPU merging.
+    int64 keys used for multi-GPU merging.  ``resident``: token of a corpus that stays unchanged in HBM, see
+    ``ResidentIndex``.
     """
     dev = _require_cuda(corpus, queries)
     if corpus.dim() != 2 or queries.dim() != 2 or corpus.shape[1] != queries.shape[1]:
@@ -125,11 +149,15 @@ def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_ba
         keys_ptr = keys.data_ptr() if keys is not None else None
         if algo == "gemm":
             need = lib.ss_cosine_topk_gemm_workspace_bytes(n, d, b, k)
-            ws = workspace(dev, need, "gemm")
-            st = lib.ss_cosine_topk_gemm(
+            ws = resident.workspace(dev, need) if resident is not None else workspace(dev, need, "gemm")
+            state = (ws.data_ptr(), corpus.data_ptr(), n, d, corpus.dtype)
+            valid = resident is not None and resident.state == state
+            st = lib.ss_cosine_topk_gemm_resident(
                 corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, k, int(index_base), ws.data_ptr(),
-                ws.numel(), keys_ptr, scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
-            _lib.check(st, "ss_cosine_topk_gemm")
+                ws.numel(), int(valid), keys_ptr, scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
+            _lib.check(st, "ss_cosine_topk_gemm_resident")
+            if resident is not None:
+                resident.state = state
         elif algo == "tcstream":
             # per-CTA partial lists cost ~148 * k * 8 bytes per query: very large batches go through in slices
             step = max(64, min(b, (_TCSTREAM_WS_BUDGET // (160 * k * 8)) // 64 * 64))

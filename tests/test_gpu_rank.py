@@ -159,3 +159,30 @@ def test_graphed_search_replays_the_eager_search():
             torch.cuda.synchronize()
             assert torch.equal(i0, i1) and torch.equal(s0, s1)
             assert int(i1.min()) >= 1000
+
+
+def test_resident_corpus_keeps_its_norms_between_gemm_searches():
+    """K2 through ShardedCorpus skips the corpus-norm pre-pass from the second search on: results must not change, two
+    corpora on one device must not see each other's norms, and invalidate() forces the pre-pass again."""
+    from semanticsearch_b200 import sharded, similarity
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn((30000, 128), generator=g, device="cuda").to(torch.bfloat16)
+    B = (torch.randn((30000, 128), generator=g, device="cuda") * 3.0).to(torch.bfloat16)   # different norms, same shape
+    Q = torch.randn((256, 128), generator=g, device="cuda").to(torch.bfloat16)
+    ca, cb = sharded.ShardedCorpus(A, 0), sharded.ShardedCorpus(B, 0)
+    want_a = similarity.cosine_topk(A, Q, 10, algo="gemm")
+    want_b = similarity.cosine_topk(B, Q, 10, algo="gemm")
+    for _ in range(3):   # first call computes the norms, the later ones reuse them; the corpora alternate
+        for corpus, want in ((ca, want_a), (cb, want_b)):
+            s, i = corpus.search(Q, 10, algo="gemm")
+            assert torch.equal(i, want[1]) and torch.equal(s, want[0])
+    assert ca._resident.state is not None and ca._resident.ws is not cb._resident.ws
+    # a smaller batch reuses the norms as well (their place in the workspace does not depend on the batch)
+    s, i = ca.search(Q[:128].contiguous(), 10, algo="gemm")
+    w = similarity.cosine_topk(A, Q[:128].contiguous(), 10, algo="gemm")
+    assert torch.equal(i, w[1]) and torch.equal(s, w[0])
+    A.mul_(0.5)                       # the corpus bytes change (cosines do not): the owner must say so
+    ca._resident.invalidate()
+    s, i = ca.search(Q, 10, algo="gemm")
+    w = similarity.cosine_topk(A, Q, 10, algo="gemm")
+    assert torch.equal(i, w[1]) and torch.equal(s, w[0])
