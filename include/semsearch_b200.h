@@ -210,6 +210,25 @@ int ss_group_threshold_pass(const float* S, const int32_t* offsets, const int64_
                             int knn_mode, float* out_sharp, double* out_centrality, double* out_doc_stats,
                             int32_t* out_knn_idx, float* out_knn_val, void* stream);
 
+/* ---- §8f-2: block sums of sim_sharp over cluster member lists, co-association of a label sweep ---------
+ * Device form of the reference's `_mean_between` / `_mean_within` double loops and of the per-(sentence, cluster)
+ * means of the reassignment pass (Method/Semantic_Grouping_Optimized.py:118-130,566-588): for every document d of a
+ * batch (sim_sharp packed like K4's output), with groups group_prefix[d]..group_prefix[d+1] and the members
+ * (document-local row indices, repeats allowed — the reference's lists are multisets) of group g at
+ * members[member_prefix[g]..member_prefix[g+1]]:
+ *   out_rowsum[rowsum_offsets[d] + x*G + g] = sum_{y in g} sim_sharp[x][y]         (float64, list order)
+ *   out_block [block_offsets[d]  + a*G + b] = sum_{x in a} rowsum[x][b]            (float64, list order)
+ * so mean_between(A,B) = block[A][B]/(|A||B|), mean_within(A) = block[A][A]/(|A|(|A|-1)) (sim_sharp is symmetric with
+ * a zero diagonal) and the reassignment mean of x against g = rowsum[x][g]/|g|.  row_doc[total_rows] = document of
+ * each row.  Summation order is fixed, results are reproducible.
+ * ss_group_coassociation: C[i][j] = #{l : labels[l][i] == labels[l][j]} / n_labelings off the diagonal, 0 on it
+ * (the consensus matrix of the Louvain resolution sweep, :231-241); labels = int32[n_labelings][n]. */
+int ss_group_block_sums(const float* sharp, const int32_t* offsets, const int64_t* s_offsets, int n_docs, int total_rows,
+                        const int32_t* row_doc, const int32_t* group_prefix, const int32_t* member_prefix,
+                        const int32_t* members, const int64_t* rowsum_offsets, const int64_t* block_offsets,
+                        double* out_rowsum, double* out_block, void* stream);
+int ss_group_coassociation(const int32_t* labels, int n_labelings, int n, double* out_C, void* stream);
+
 /* Similarity-distribution statistics of each document's strict upper triangle of S (layout of K3):
  * values >= 1 - eps are dropped, then out_stats[d] = {count, min, max, mean, std, p10, p25, p50, p75,
  * p80, p85, p90, p95} with numpy's float32 percentile arithmetic.  Device form of

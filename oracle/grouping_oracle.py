@@ -129,3 +129,23 @@ def knn_graph_mismatches(W_a: np.ndarray, W_b: np.ndarray, sharp: np.ndarray, kk
             continue
         bad.append((int(i), int(j)))
     return bad
+
+
+def block_sums_ref(sharp: np.ndarray, groups) -> Tuple[np.ndarray, np.ndarray]:
+    """numpy statement of ss_group_block_sums for one document: ``rowsum[x, g] = sum(sharp[x, members_g])``,
+    ``block[a, b] = sum(sharp[np.ix_(members_a, members_b)])`` in float64 (member lists are multisets).  The reference
+    reaches the same sums element by element inside ``_mean_between`` / ``_mean_within`` (Grouping:118-130) and the
+    reassignment loop (:566-588)."""
+    S = np.asarray(sharp, dtype=np.float64)
+    n, g = S.shape[0], len(groups)
+    rowsum = np.zeros((n, g), dtype=np.float64)
+    block = np.zeros((g, g), dtype=np.float64)
+    for j, members in enumerate(groups):
+        idx = np.asarray(list(members), dtype=np.int64)
+        if idx.size:
+            rowsum[:, j] = S[:, idx].sum(axis=1)
+    for i, members in enumerate(groups):
+        idx = np.asarray(list(members), dtype=np.int64)
+        if idx.size:
+            block[i, :] = rowsum[idx, :].sum(axis=0)
+    return rowsum, block

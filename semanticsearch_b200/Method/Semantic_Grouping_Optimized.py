@@ -20,7 +20,7 @@ import json
 import math
 import re
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -61,6 +61,7 @@ class DevicePass:
     k_all: int
     knn_idx: np.ndarray      # n x 33 int32
     knn_val: np.ndarray      # n x 33 float32
+    block_sums: Optional[Callable] = None   # groups -> (rowsum [n, G], block [G, G]) float64: ragged.DocBlockSums on the device
 
 
 def device_pass_batch(doc_embeddings: Sequence[np.ndarray], tau: float = 0.15, knn_mode: int = 0) -> List[Optional[DevicePass]]:
@@ -83,6 +84,7 @@ def device_pass_batch(doc_embeddings: Sequence[np.ndarray], tau: float = 0.15, k
     stats_h = res["doc_stats"].cpu().numpy()
     kidx_h = res["knn_idx"].cpu().numpy()
     kval_h = res["knn_val"].cpu().numpy()
+    sharp_d = res["sim_sharp"]   # stays on the device: the host stage asks for block sums over it (ss_group_block_sums)
     for slot, d in enumerate(live):
         n = sizes[d]
         a, b = plan.s_offsets[slot], plan.s_offsets[slot + 1]
@@ -92,28 +94,47 @@ def device_pass_batch(doc_embeddings: Sequence[np.ndarray], tau: float = 0.15, k
             sim_matrix=S_h[a:b].reshape(n, n).copy(), sim_sharp=sharp_h[a:b].reshape(n, n).copy(),
             centrality=cent_h[r0:r1].copy(), mu=float(st[0]), sigma=float(st[1]), q80=float(st[2]), q65=float(st[3]),
             q60=float(st[4]), reassign_delta=float(st[5]), n_positive=int(st[6]), k_all=int(st[7]),
-            knn_idx=kidx_h[r0:r1].copy(), knn_val=kval_h[r0:r1].copy())
+            knn_idx=kidx_h[r0:r1].copy(), knn_val=kval_h[r0:r1].copy(),
+            block_sums=ragged.DocBlockSums(sharp_d[int(a):int(b)], n))
     return out
 
 
 # ----------------------------------------------------------------------------------------------
 # Host stage: block means, spectral clustering, k-means
 # ----------------------------------------------------------------------------------------------
-def _mean_between(sharp: np.ndarray, A: List[int], B: List[int]) -> float:
-    """Reference :118-121 — fp64 mean of sim_sharp over A x B (row-major), 0.0 if either is empty."""
-    if not A or not B:
-        return 0.0
-    return float(np.mean(sharp[np.ix_(A, B)].astype(np.float64).ravel()))
+class _GroupMeans:
+    """Every block mean the clustering stage needs for one list of groups, from ONE launch of ss_group_block_sums
+    (reference `_mean_between` / `_mean_within`, :118-130).  Groups are multisets of sentence indices; sums over unions
+    of groups are sums of their blocks, so merged candidates need no further launch.  `sim_sharp` is bit-symmetric with
+    a zero diagonal (K3 mirrors its tiles, K4 sharpens element-wise), hence the i < j pairs of a group are half of its
+    full block."""
+
+    def __init__(self, block_sums: Callable, groups: Sequence[Sequence[int]]):
+        self.sizes = [len(g) for g in groups]
+        self.rowsum, self.block = block_sums([list(g) for g in groups])
+
+    def between(self, a: Sequence[int], b: Sequence[int]) -> float:
+        """mean over (union of groups a) x (union of groups b); 0.0 if either side is empty (:119-120)."""
+        la, lb = sum(self.sizes[i] for i in a), sum(self.sizes[j] for j in b)
+        if not la or not lb:
+            return 0.0
+        return float(sum(self.block[i, j] for i in a for j in b) / (la * lb))
+
+    def within(self, a: Sequence[int]) -> float:
+        """mean over the unordered pairs of the union of groups a; 1.0 for fewer than two members (:124-125)."""
+        m = sum(self.sizes[i] for i in a)
+        if m <= 1:
+            return 1.0
+        return float(sum(self.block[i, j] for i in a for j in a) / (m * (m - 1)))
 
 
-def _mean_within(sharp: np.ndarray, A: List[int]) -> float:
-    """Reference :123-130 — fp64 mean over unordered pairs i < j, 1.0 for |A| <= 1."""
-    m = len(A)
-    if m <= 1:
-        return 1.0
-    sub = sharp[np.ix_(A, A)].astype(np.float64)
-    vals = sub[np.triu_indices(m, 1)]
-    return float(np.mean(vals)) if vals.size else 1.0
+def _louvain_available() -> bool:
+    try:
+        import networkx  # type: ignore # noqa: F401
+        import community  # type: ignore # noqa: F401
+        return True
+    except Exception:
+        return False
 
 
 def _normalized_laplacian(W: np.ndarray) -> np.ndarray:
@@ -121,8 +142,9 @@ def _normalized_laplacian(W: np.ndarray) -> np.ndarray:
     d = np.sum(W, axis=1)
     with np.errstate(divide="ignore"):
         d_inv_sqrt = np.where(d > 0, 1.0 / np.sqrt(d), 0.0)
-    D = np.diag(d_inv_sqrt)
-    return np.eye(W.shape[0], dtype=float) - (D @ W @ D)
+    # (D @ W @ D)[i, j] = (d_i * W_ij) * d_j: the products with D's zeros add exact zeros, so scaling rows then columns
+    # gives the reference's matrix bit for bit without its two n^3 products
+    return np.eye(W.shape[0], dtype=float) - ((d_inv_sqrt[:, None] * W) * d_inv_sqrt[None, :])
 
 
 def _kmeans(X: np.ndarray, k: int, n_init: int = 5, max_iter: int = 100, seed: int = 0) -> np.ndarray:
@@ -225,11 +247,8 @@ def _modularity_multiscale_labels(S_filtered, gamma_start, gamma_end, gamma_step
     if not label_list:
         return None
     try:
-        C = np.zeros((n_local, n_local), dtype=float)
-        for lab in label_list:
-            C += (lab[:, None] == lab[None, :]).astype(float)
-        np.fill_diagonal(C, 0.0)
-        C = C / float(len(label_list))
+        from ..ragged import group_coassociation
+        C = group_coassociation(np.stack(label_list)).cpu().numpy()   # ss_group_coassociation (reference :231-241)
         thr = float(np.quantile(C[np.triu_indices(n_local, 1)], 0.5)) if n_local > 1 else 0.0
         Wc = np.where(C >= thr, C, 0.0)
         Wc = np.maximum(Wc, Wc.T)
@@ -252,11 +271,17 @@ def cluster_from_device_pass(dp: DevicePass, *, auto_params: bool = True, knn_k:
                              spectral_kmax: Optional[int] = None, rmt_keep_eigs: int = 3, mod_gamma_start: float = 0.7,
                              mod_gamma_end: float = 1.6, mod_gamma_step: float = 0.15, cap_soft: Optional[int] = None,
                              small_group_min: int = 2, tau_merge: float = 0.38, reassign_delta: float = 0.02,
-                             engine: Optional[str] = None,
-                             W_override: Optional[np.ndarray] = None) -> Tuple[List[List[int]], str, np.ndarray]:
+                             engine: Optional[str] = None, W_override: Optional[np.ndarray] = None,
+                             block_sums: Optional[Callable] = None) -> Tuple[List[List[int]], str, np.ndarray]:
     """Reference :343-588 on the device outputs.  Returns (clusters, method_used, W_all).
-    ``W_override`` substitutes a pre-built kNN graph (tests pin the host stage with the reference's own W)."""
+    ``W_override`` substitutes a pre-built kNN graph (tests pin the host stage with the reference's own W).
+    ``block_sums`` (default: the device pass's own ``ragged.DocBlockSums``) maps a list of member lists to
+    ``(rowsum, block)``; every block mean of the merge / refine / reassign phases is derived from its output."""
     from ..ragged import knn_graph_from_lists
+    sums = block_sums or dp.block_sums
+    if sums is None:
+        raise RuntimeError("the clustering stage needs the device block sums of sim_sharp (ss_group_block_sums); "
+                           "there is no CPU fallback")
     sharp = dp.sim_sharp
     n = sharp.shape[0]
     has_pos = dp.n_positive > 0
@@ -274,11 +299,14 @@ def cluster_from_device_pass(dp: DevicePass, *, auto_params: bool = True, knn_k:
         method_used = "SpectralOnly"
         labels = _auto_k_spectral_labels(W_all, kmax=kmax_eff)
     else:
-        try:
-            labels = _modularity_multiscale_labels(_rmt_filter(sharp, int(max(1, rmt_keep_eigs))), float(mod_gamma_start),
-                                                   float(mod_gamma_end), float(mod_gamma_step), eff_edge_floor, kmax_eff)
-        except Exception:
-            labels = None
+        # without networkx + python-louvain the modularity engine returns None whatever its input (reference :192-195,
+        # 265-267): the eigendecomposition of the RMT filter is then skipped, the outcome is the same
+        if _louvain_available():
+            try:
+                labels = _modularity_multiscale_labels(_rmt_filter(sharp, int(max(1, rmt_keep_eigs))), float(mod_gamma_start),
+                                                       float(mod_gamma_end), float(mod_gamma_step), eff_edge_floor, kmax_eff)
+            except Exception:
+                labels = None
         if labels is None:
             method_used = "SpectralFallback"
             labels = _auto_k_spectral_labels(W_all, kmax=kmax_eff)
@@ -297,6 +325,7 @@ def cluster_from_device_pass(dp: DevicePass, *, auto_params: bool = True, knn_k:
         eff_cap_soft = int(cap_soft if cap_soft is not None else max(20, n // 3))
 
     def bisect(members: List[int]):
+        """(left, right, within(left), within(right)) when the two spectral halves separate (sep < 0), else None."""
         if len(members) < 4:
             return None
         try:
@@ -308,14 +337,16 @@ def cluster_from_device_pass(dp: DevicePass, *, auto_params: bool = True, knn_k:
         right = [m for m, l in zip(members, lab2) if l == 1]
         if not left or not right:
             return None
-        sep = _mean_between(sharp, left, right) - 0.5 * (_mean_within(sharp, left) + _mean_within(sharp, right))
-        return (sorted(left), sorted(right)) if sep < 0.0 else None
+        gm = _GroupMeans(sums, [left, right])
+        w_left, w_right = gm.within([0]), gm.within([1])
+        sep = gm.between([0], [1]) - 0.5 * (w_left + w_right)
+        return (sorted(left), sorted(right), w_left, w_right) if sep < 0.0 else None
 
     split_groups: List[List[int]] = []
     for g in groups:
         halves = bisect(g) if len(g) > eff_cap_soft else None
-        if halves is not None and all(len(x) >= max(2, small_group_min) for x in halves):
-            split_groups.extend(list(halves))
+        if halves is not None and all(len(x) >= max(2, small_group_min) for x in halves[:2]):
+            split_groups.extend([halves[0], halves[1]])
         else:
             split_groups.append(sorted(g))
     groups = split_groups
@@ -330,6 +361,7 @@ def cluster_from_device_pass(dp: DevicePass, *, auto_params: bool = True, knn_k:
         eff_tau_merge = float(tau_merge)
     merged: List[List[int]] = []
     consumed = set()
+    gm = _GroupMeans(sums, groups) if any(len(g) < max(2, int(min_len)) for g in groups) else None  # one launch for the phase
     for i, g in enumerate(groups):
         if i in consumed:
             continue
@@ -340,9 +372,9 @@ def cluster_from_device_pass(dp: DevicePass, *, auto_params: bool = True, knn_k:
         for j, h in enumerate(groups):
             if j == i or j in consumed:
                 continue
-            if _mean_between(sharp, g, h) < float(eff_tau_merge):
+            if gm.between([i], [j]) < float(eff_tau_merge):
                 continue
-            gain = _mean_within(sharp, sorted(g + h)) - 0.5 * (_mean_within(sharp, g) + _mean_within(sharp, h))
+            gain = gm.within([i, j]) - 0.5 * (gm.within([i]) + gm.within([j]))
             if gain > best_gain:
                 best_gain, best_j = gain, j
         if best_j is not None and best_gain > 0.0:
@@ -353,58 +385,80 @@ def cluster_from_device_pass(dp: DevicePass, *, auto_params: bool = True, knn_k:
 
     # ---- refine: split loose clusters, merge near-duplicate neighbours (reference :494-553) ------
     try:
-        internal = [float(_mean_within(sharp, g)) for g in merged]
+        gm = _GroupMeans(sums, merged)
+        internal = [gm.within([i]) for i in range(len(merged))]
         low_thr = float(np.percentile(np.array(internal, dtype=float), 25)) if len(internal) >= 2 else 0.0
         refined: List[List[int]] = []
-        for g in merged:
-            if len(g) >= 6 and float(_mean_within(sharp, g)) < max(0.5, low_thr):
+        for i, g in enumerate(merged):
+            if len(g) >= 6 and internal[i] < max(0.5, low_thr):
                 halves = bisect(g)
-                if halves is not None:
-                    parent = float(_mean_within(sharp, g))
-                    if float(_mean_within(sharp, halves[0])) > parent and float(_mean_within(sharp, halves[1])) > parent:
-                        refined.append(sorted(halves[0]))
-                        refined.append(sorted(halves[1]))
-                        continue
+                if halves is not None and halves[2] > internal[i] and halves[3] > internal[i]:
+                    refined.append(halves[0])
+                    refined.append(halves[1])
+                    continue
             refined.append(g)
         global_merge_thr = dp.q60 if has_pos else 0.5
+        gm = _GroupMeans(sums, refined)
         merged_adj: List[List[int]] = []
         i = 0
         while i < len(refined):
             cur = refined[i]
+            span = [i]                       # `cur` is the multiset union of refined[i .. j-1]
             j = i + 1
             while j < len(refined):
-                inter = _mean_between(sharp, cur, refined[j])
-                cmp_thr = 0.9 * min(max(float(_mean_within(sharp, cur)), 1e-6), max(float(_mean_within(sharp, refined[j])), 1e-6))
+                inter = gm.between(span, [j])
+                cmp_thr = 0.9 * min(max(gm.within(span), 1e-6), max(gm.within([j]), 1e-6))
                 if inter >= max(cmp_thr, global_merge_thr):
                     cur = sorted(cur + refined[j])
+                    span.append(j)
                     j += 1
                 else:
                     break
             merged_adj.append(cur)
             i = j
         merged = merged_adj
+    except RuntimeError:
+        raise                                # device errors are never swallowed (no CPU fallback)
     except Exception:
         pass
 
     # ---- one-pass sentence reassignment (reference :555-588) -----------------------------------
     if len(merged) >= 2:
         delta = (dp.reassign_delta if has_pos else float(reassign_delta)) if auto_params else float(reassign_delta)
+        n_c = len(merged)
+        R = np.array(_GroupMeans(sums, merged).rowsum, dtype=np.float64)   # R[x, c] = sum of sim_sharp[x, members of c]
+        occ = np.zeros((n_c, n), dtype=np.int64)                           # occ[c, y] = how often y is listed in cluster c
+        for c, g in enumerate(merged):
+            for y in g:
+                if 0 <= y < n:
+                    occ[c, y] += 1
+        sizes_c = [len(g) for g in merged]
         for x in range(n):
-            cur = next((cid for cid, g in enumerate(merged) if x in g), None)
-            if cur is None:
+            holders = np.flatnonzero(occ[:, x])
+            if holders.size == 0:
                 continue
-            members = [y for y in merged[cur] if y != x]
+            cur = int(holders[0])
+            m_cur = sizes_c[cur] - int(occ[cur, x])        # members of `cur` other than x; sim_sharp[x, x] == 0
             best_c = cur
-            best_score = float(np.mean(sharp[x, members].astype(np.float64))) if members else 0.0
-            for c2, h in enumerate(merged):
+            best_score = float(R[x, cur] / m_cur) if m_cur else 0.0
+            row = R[x]
+            for c2 in range(n_c):
                 if c2 == cur:
                     continue
-                other = float(np.mean(sharp[x, h].astype(np.float64))) if h else 0.0
+                other = float(row[c2] / sizes_c[c2]) if sizes_c[c2] else 0.0
                 if other > best_score + float(delta):
                     best_score, best_c = other, c2
             if best_c != cur:
+                removed = int(occ[cur, x])
                 merged[cur] = [y for y in merged[cur] if y != x]
                 merged[best_c] = sorted(merged[best_c] + [x])
+                col = sharp[:, x].astype(np.float64)       # the sums of the two clusters change by x's column
+                R[:, cur] -= removed * col
+                R[:, best_c] += col
+                occ[cur, x] = 0
+                occ[best_c, x] += 1
+                sizes_c[cur] -= removed
+                sizes_c[best_c] += 1
     return merged, method_used, W_all
 
 

@@ -15,7 +15,7 @@
 //
 // The B x N score matrix is never written.  Work is split into (query block, corpus chunk) units
 // so that all query blocks of one chunk run concurrently and share corpus tiles through L2; each
-// unit writes k packed keys per query and ss_topk_merge folds the chunks.
+// unit publishes its finds into one global best-first key list per query (lock-free, see publish_key).
 #include <algorithm>
 #include <cstdlib>
 
@@ -59,8 +59,7 @@ struct GemmParams {
   const float* inv_c;  // padded to a multiple of G_BN entries, NaN past n_rows (never selected)
   const float* inv_gmax;  // [n_fill / 32] largest 1/|c| of each 32-row group (NaN rows ignored)
   const float* inv_q;
-  uint64_t* partial;  // [n_chunks * 2][n_queries][k]: one list per (chunk, column half)
-  uint32_t* gthr;     // [n_queries] best published k-th score per query (order-preserving bits), zeroed before launch
+  uint64_t* gtop;  // [n_queries][k] global best-first key list of every query, zeroed before launch (see publish_list)
 };
 
 // Per-thread top-k list in shared memory, entry j of epilogue thread e at list[j * 128 + e]
@@ -83,6 +82,21 @@ __device__ __noinline__ float epi_list_insert(ScoreIdx* list, int k, float sc, i
   e.ix = c;
   list[j * G_EPI_THREADS] = e;
   return list[(k - 1) * G_EPI_THREADS].v;
+}
+
+// Global per-query result list, shared by every unit of the launch: gtop[query][0..k) holds packed keys, best first.
+// A unit publishes a key with a cascade of 64-bit atomicMax operations — slot s keeps the larger of (its key, the
+// incoming key) and hands the smaller one to slot s + 1.  Slots only grow, what a slot hands down never exceeds what
+// it keeps, and every key lives in exactly one place (a slot or the register of one cascade in flight), so at ANY moment
+// the array is sorted and its non-empty slots are distinct real rows: gtop[query][k-1] != 0 proves that k rows score at
+// least that much, i.e. it is a sound lower bound of the final k-th best, and after the last cascade the array is the
+// exact top-k by (score desc, row asc) whatever the interleaving.  Units read that bound when they start, so only the
+// first wave of units runs with cold thresholds, and no per-unit partial lists or merge pass exist.
+__device__ __forceinline__ void publish_key(unsigned long long* g, int k, unsigned long long x) {
+  for (int s = 0; s < k && x != 0ull; ++s) {
+    const unsigned long long old = atomicMax(g + s, x);
+    x = old < x ? old : x;
+  }
 }
 
 // One 32-column group of one query row.  Cheap bound first: with a non-negative threshold no column can
@@ -258,13 +272,12 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         e.ix = -1;
         my_list[j * G_EPI_THREADS] = e;
       }
-      // Seed the threshold with the best k-th score an EARLIER unit of this query has published: whoever
-      // holds k rows scoring >= v proves that rows scoring < v cannot reach the global top-k, so the
-      // warm-up inserts of the first wave of (chunk, half) lists are not repeated by the later waves.
-      // One step below v: equal scores still compete on the row index.
+      // Seed the threshold with the k-th best score published so far for this query (all units, all chunks): rows
+      // scoring below it cannot reach the global top-k.  One step below: equal scores still compete on the row index.
       float thr = -INFINITY;
-      if (p.gthr != nullptr && query < p.n_queries) {
-        const uint32_t g = *reinterpret_cast<volatile uint32_t*>(p.gthr + query);
+      unsigned long long* gq = reinterpret_cast<unsigned long long*>(p.gtop) + static_cast<size_t>(query < p.n_queries ? query : 0) * p.k;
+      if (query < p.n_queries) {
+        const uint32_t g = static_cast<uint32_t>(*reinterpret_cast<volatile unsigned long long*>(gq + p.k - 1) >> 32);
         if (g > 1u) thr = ordered_to_float(g - 1u);
       }
       const float thr_floor = thr;
@@ -299,12 +312,13 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
       }
       if (query < p.n_queries) {
-        const float kth = my_list[(p.k - 1) * G_EPI_THREADS].v;  // -inf unless this list holds k rows
-        if (p.gthr != nullptr && kth > thr_floor) atomicMax(p.gthr + query, float_to_ordered(kth));
-        uint64_t* out = p.partial + ((static_cast<size_t>(chunk) * 2 + half) * p.n_queries + query) * p.k;
+        // publish what this unit found: the list is best-first, so the first entry that cannot enter ends the walk
         for (int j = 0; j < p.k; ++j) {
           const ScoreIdx e = my_list[j * G_EPI_THREADS];
-          out[j] = e.ix >= 0 ? make_key(e.v, p.index_base + static_cast<uint32_t>(e.ix)) : 0ull;
+          if (e.ix < 0) break;
+          const unsigned long long key = make_key(e.v, p.index_base + static_cast<uint32_t>(e.ix));
+          if (key <= *reinterpret_cast<volatile unsigned long long*>(gq + p.k - 1)) break;
+          publish_key(gq, p.k, key);
         }
       }
     }
@@ -316,6 +330,17 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     tc_fence_after();
     if (CG == 2) tmem_dealloc_pair(tmem_base, G_TMEM_COLS); else tmem_dealloc(tmem_base, G_TMEM_COLS);
   }
+}
+
+// Final form of the global lists: packed keys -> (keys, scores, indices); empty slots read -inf / -1.
+__global__ void __launch_bounds__(256) decode_keys_kernel(const uint64_t* __restrict__ keys, long long n, uint64_t* __restrict__ out_keys,
+                                                          float* __restrict__ out_scores, long long* __restrict__ out_indices) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];
+  if (out_keys) out_keys[i] = key;
+  if (out_scores) out_scores[i] = key ? key_score(key) : -INFINITY;
+  if (out_indices) out_indices[i] = key ? key_index(key) : -1;
 }
 
 // ---- vectorised row inverse norms (pre-pass over the corpus, HBM-bound) -------------------------
@@ -424,10 +449,14 @@ static GemmPlan make_gemm_plan(long long n_rows, int n_queries) {
   const int cg = gemm_cta_group(n_queries);
   g.n_qb = (n_queries + G_BM * cg - 1) / (G_BM * cg);
   g.n_tiles = (n_rows + G_BN - 1) / G_BN;
-  static const int units_per_worker = getenv("SS_GEMM_UNITS_PER_WORKER") ? std::max(1, atoi(getenv("SS_GEMM_UNITS_PER_WORKER"))) : 8;
+  // Short units keep the query blocks that share a corpus chunk inside an L2-sized window (their drift is bounded by the
+  // unit length); the global result lists make a unit start cheap (one threshold read per query).  Measured on B200
+  // (profiles/r02_k2_units_sweep.txt): chunks of ~8 tiles (3 MB of corpus) are the optimum at 1.25 M and at 10 M rows.
+  static const int units_per_worker = getenv("SS_GEMM_UNITS_PER_WORKER") ? std::max(1, atoi(getenv("SS_GEMM_UNITS_PER_WORKER"))) : 1024;
   const long long target_units = static_cast<long long>(sm_count() / cg) * units_per_worker;
   long long n_chunks = std::max<long long>(1, (target_units + g.n_qb - 1) / g.n_qb);
-  n_chunks = std::min<long long>(n_chunks, std::max<long long>(1, g.n_tiles / 8));  // at least ~8 tiles per chunk
+  static const int min_tiles = getenv("SS_GEMM_MIN_TILES") ? std::max(1, atoi(getenv("SS_GEMM_MIN_TILES"))) : 8;
+  n_chunks = std::min<long long>(n_chunks, std::max<long long>(1, g.n_tiles / min_tiles));  // at least ~min_tiles tiles per chunk
   g.tiles_per_chunk = static_cast<int>((g.n_tiles + n_chunks - 1) / n_chunks);
   g.n_chunks = static_cast<int>((g.n_tiles + g.tiles_per_chunk - 1) / g.tiles_per_chunk);
   return g;
@@ -441,9 +470,9 @@ extern "C" size_t ss_cosine_topk_gemm_workspace_bytes(int64_t n_rows, int dim, i
   (void)dim;
   if (n_rows <= 0 || n_queries <= 0 || k <= 0) return 0;
   const GemmPlan g = make_gemm_plan(n_rows, n_queries);
+  (void)g;
   return align_up(static_cast<size_t>(n_rows), G_BN) * 4 + align_up(align_up(static_cast<size_t>(n_rows), G_BN) / 32 * 4, 256) +
-         align_up(static_cast<size_t>(n_queries) * 4, 256) +
-         align_up(static_cast<size_t>(g.n_chunks) * 2 * n_queries * k * 8, 256) + align_up(static_cast<size_t>(n_queries) * 4, 256) + 256;
+         align_up(static_cast<size_t>(n_queries) * 4, 256) + align_up(static_cast<size_t>(n_queries) * k * 8, 256) + 256;
 }
 
 // corpus_norms_valid: the head of `workspace` (inverse norms of the corpus rows and their 32-row group maxima, whose
@@ -472,13 +501,8 @@ static int cosine_topk_gemm_impl(const void* corpus, int64_t n_rows, int dim, in
   ws += align_up(static_cast<size_t>(n_fill) / 32 * 4, 256);
   float* inv_q = reinterpret_cast<float*>(ws);
   ws += align_up(static_cast<size_t>(n_queries) * 4, 256);
-  uint64_t* partial = reinterpret_cast<uint64_t*>(ws);
-  {
-    const GemmPlan g0 = make_gemm_plan(n_rows, n_queries);
-    ws += align_up(static_cast<size_t>(g0.n_chunks) * 2 * n_queries * k * 8, 256);
-  }
-  uint32_t* gthr = reinterpret_cast<uint32_t*>(ws);
-  SS_CUDA_CHECK(cudaMemsetAsync(gthr, 0, static_cast<size_t>(n_queries) * 4, st));
+  uint64_t* gtop = reinterpret_cast<uint64_t*>(ws);
+  SS_CUDA_CHECK(cudaMemsetAsync(gtop, 0, static_cast<size_t>(n_queries) * k * 8, st));
 
   cudaError_t e = cudaSuccess;
   if (dtype == SS_BF16) {
@@ -516,8 +540,7 @@ static int cosine_topk_gemm_impl(const void* corpus, int64_t n_rows, int dim, in
   p.inv_c = inv_c;
   p.inv_gmax = inv_gmax;
   p.inv_q = inv_q;
-  p.partial = partial;
-  p.gthr = getenv("SS_GEMM_NO_SHARE") ? nullptr : gthr;
+  p.gtop = gtop;
   const uint32_t idesc = make_idesc(dtype == SS_BF16 ? 1 : 0, G_BM * cg, G_BN);
   const size_t per_stage = cg == 2 ? GemmCfg<2>::kStageBytes : GemmCfg<1>::kStageBytes;
   const size_t fixed = 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4 + 2 * (G_BN / 32) * 4 + static_cast<size_t>(k) * G_EPI_THREADS * sizeof(ScoreIdx);
@@ -552,8 +575,11 @@ static int cosine_topk_gemm_impl(const void* corpus, int64_t n_rows, int dim, in
     }
   }
   if (e != cudaSuccess) return cuda_fail(e, "cosine_topk_gemm launch");
-  return ss_topk_merge(partial, g.n_chunks * 2, n_queries, k, k, static_cast<int64_t>(n_queries) * k, k, out_keys, out_scores,
-                       out_indices, stream);
+  const long long n_keys = static_cast<long long>(n_queries) * k;
+  decode_keys_kernel<<<static_cast<unsigned int>((n_keys + 255) / 256), 256, 0, st>>>(gtop, n_keys, out_keys, out_scores,
+                                                                                     reinterpret_cast<long long*>(out_indices));
+  SS_CUDA_CHECK(cudaGetLastError());
+  return SS_OK;
 }
 
 extern "C" int ss_cosine_topk_gemm(const void* corpus, int64_t n_rows, int dim, int dtype, const void* queries, int n_queries,

@@ -143,6 +143,117 @@ def group_threshold_pass(S: torch.Tensor, plan: RaggedPlan, tau: float = 0.15, k
     return {"sim_sharp": sharp, "centrality": cent, "doc_stats": stats, "knn_idx": kidx, "knn_val": kval}
 
 
+def group_block_sums(sharp: torch.Tensor, plan: RaggedPlan, groups_per_doc: Sequence[Sequence[Sequence[int]]]):
+    """Block sums of ``sim_sharp`` over member lists for every document of a batch — the device form of the reference's
+    ``_mean_between`` / ``_mean_within`` loops and reassignment means (Method/Semantic_Grouping_Optimized.py:118-130,
+    566-588).  ``groups_per_doc[d]`` = the member lists (document-local sentence indices, repeats allowed) of document d.
+    Returns one ``(rowsum float64 [n, G], block float64 [G, G])`` pair of host arrays per document:
+    ``rowsum[x, g] = sum(sharp[x, members_g])``, ``block[a, b] = sum(sharp[np.ix_(members_a, members_b)])``."""
+    dev = _require_cuda(sharp)
+    if sharp.dtype != torch.float32 or not sharp.is_contiguous() or sharp.numel() < plan.total_s:
+        raise ValueError("sharp must be the packed float32 sim_sharp output of group_threshold_pass")
+    if len(groups_per_doc) != plan.n_docs:
+        raise ValueError("one list of member lists per document")
+    sizes = plan.sizes()
+    gcount = np.array([len(g) for g in groups_per_doc], dtype=np.int64)
+    group_prefix = np.zeros(plan.n_docs + 1, dtype=np.int32)
+    group_prefix[1:] = np.cumsum(gcount)
+    flat = [np.asarray(m, dtype=np.int32).reshape(-1) for gs in groups_per_doc for m in gs]
+    member_prefix = np.zeros(len(flat) + 1, dtype=np.int32)
+    if flat:
+        member_prefix[1:] = np.cumsum([m.size for m in flat])
+    members = np.concatenate(flat) if flat and member_prefix[-1] > 0 else np.zeros(1, dtype=np.int32)
+    rs_off = np.zeros(plan.n_docs + 1, dtype=np.int64)
+    rs_off[1:] = np.cumsum(sizes.astype(np.int64) * gcount)
+    blk_off = np.zeros(plan.n_docs + 1, dtype=np.int64)
+    blk_off[1:] = np.cumsum(gcount * gcount)
+    out = []
+    if plan.total_rows == 0 or int(group_prefix[-1]) == 0:
+        return [(np.zeros((int(n), int(g))), np.zeros((int(g), int(g)))) for n, g in zip(sizes, gcount)]
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        row_doc = torch.repeat_interleave(torch.arange(plan.n_docs, dtype=torch.int32, device=dev),
+                                          (plan.offsets_d[1:] - plan.offsets_d[:-1]).to(torch.int64))
+        packed = np.concatenate([group_prefix.view(np.int32), member_prefix, members])   # one H2D copy for the three index arrays
+        packed_d = torch.from_numpy(packed).to(dev)
+        gp_d = packed_d[: group_prefix.size]
+        mp_d = packed_d[group_prefix.size: group_prefix.size + member_prefix.size]
+        mem_d = packed_d[group_prefix.size + member_prefix.size:]
+        offs_d = torch.from_numpy(np.concatenate([rs_off[:-1], blk_off[:-1]])).to(dev)
+        rowsum = torch.empty(max(int(rs_off[-1]), 1), dtype=torch.float64, device=dev)
+        block = torch.empty(max(int(blk_off[-1]), 1), dtype=torch.float64, device=dev)
+        st = lib.ss_group_block_sums(sharp.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), plan.n_docs,
+                                     plan.total_rows, row_doc.data_ptr(), gp_d.data_ptr(), mp_d.data_ptr(), mem_d.data_ptr(),
+                                     offs_d.data_ptr(), offs_d[plan.n_docs:].data_ptr(), rowsum.data_ptr(), block.data_ptr(),
+                                     _stream_ptr(dev))
+        _lib.check(st, "ss_group_block_sums")
+        rs_h, blk_h = rowsum.cpu().numpy(), block.cpu().numpy()
+    for d in range(plan.n_docs):
+        n, g = int(sizes[d]), int(gcount[d])
+        out.append((rs_h[rs_off[d]:rs_off[d + 1]].reshape(n, g), blk_h[blk_off[d]:blk_off[d + 1]].reshape(g, g)))
+    return out
+
+
+class DocBlockSums:
+    """``group_block_sums`` bound to ONE document whose ``sim_sharp`` stays on the device: the host clustering stage calls
+    it a handful of times per document (once per merge / refine / reassign phase, once per bisection), each call being
+    one small H2D copy of the member lists, two launches and one D2H copy of the sums."""
+
+    def __init__(self, sharp_doc: torch.Tensor, n: int):
+        dev = _require_cuda(sharp_doc)
+        if sharp_doc.dtype != torch.float32 or not sharp_doc.is_contiguous() or sharp_doc.numel() < n * n:
+            raise ValueError("sharp_doc must be a contiguous float32 CUDA tensor holding the document's n x n sim_sharp")
+        self.sharp, self.n, self.dev = sharp_doc, int(n), dev
+        with torch.cuda.device(dev):
+            self.offsets_d = torch.tensor([0, self.n], dtype=torch.int32, device=dev)
+            self.s_offsets_d = torch.tensor([0, self.n * self.n], dtype=torch.int64, device=dev)
+            self.row_doc = torch.zeros(max(self.n, 1), dtype=torch.int32, device=dev)
+            self.zero_off = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.calls = 0
+
+    def __call__(self, groups: Sequence[Sequence[int]]):
+        """``(rowsum float64 [n, G], block float64 [G, G])`` for the member lists ``groups`` (repeats allowed)."""
+        g = len(groups)
+        n = self.n
+        if g == 0 or n == 0:
+            return np.zeros((n, g)), np.zeros((g, g))
+        sizes = [len(m) for m in groups]
+        packed = np.zeros(2 + g + 1 + max(sum(sizes), 1), dtype=np.int32)
+        packed[1] = g                                   # group_prefix = [0, G]
+        packed[3:3 + g] = np.cumsum(sizes)              # member_prefix = [0, ...]
+        if sum(sizes):
+            packed[3 + g:3 + g + sum(sizes)] = np.concatenate([np.asarray(m, dtype=np.int32).reshape(-1) for m in groups if len(m)])
+        lib = _lib.load()
+        with torch.cuda.device(self.dev):
+            pk = torch.from_numpy(packed).to(self.dev)
+            out = torch.empty(n * g + g * g, dtype=torch.float64, device=self.dev)
+            st = lib.ss_group_block_sums(self.sharp.data_ptr(), self.offsets_d.data_ptr(), self.s_offsets_d.data_ptr(), 1, n,
+                                         self.row_doc.data_ptr(), pk.data_ptr(), pk[2:].data_ptr(), pk[3 + g:].data_ptr(),
+                                         self.zero_off.data_ptr(), self.zero_off.data_ptr(), out.data_ptr(),
+                                         out[n * g:].data_ptr(), _stream_ptr(self.dev))
+            _lib.check(st, "ss_group_block_sums")
+            h = out.cpu().numpy()
+        self.calls += 1
+        return h[: n * g].reshape(n, g), h[n * g:].reshape(g, g)
+
+
+def group_coassociation(labels) -> torch.Tensor:
+    """Consensus matrix of a sweep of labelings (Method/Semantic_Grouping_Optimized.py:231-241): ``labels`` int
+    ``[L, n]`` (host or device) -> float64 ``[n, n]`` device tensor, ``C[i, j]`` = share of labelings that put i and
+    j together, zero diagonal."""
+    lab = torch.as_tensor(np.asarray(labels) if not isinstance(labels, torch.Tensor) else labels)
+    if lab.dim() != 2 or lab.shape[0] < 1 or lab.shape[1] < 1:
+        raise ValueError("labels must be a non-empty [labelings, n] integer array")
+    lab = lab.to(device="cuda", dtype=torch.int32).contiguous()
+    dev = _require_cuda(lab)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        out = torch.empty((lab.shape[1], lab.shape[1]), dtype=torch.float64, device=dev)
+        _lib.check(lib.ss_group_coassociation(lab.data_ptr(), lab.shape[0], lab.shape[1], out.data_ptr(), _stream_ptr(dev)),
+                   "ss_group_coassociation")
+    return out
+
+
 STAT_KEYS = ("min", "max", "mean", "std", "p10", "p25", "p50", "p75", "p80", "p85", "p90", "p95")
 
 

@@ -32,7 +32,8 @@ def test_host_stage_reproduces_reference_clusters(golden_dir, name):
     g = np.load(os.path.join(golden_dir, "grouping.npz"))
     meta = json.loads(str(g["meta_json"]))
     dp = _device_pass_from_golden(g, meta, name)
-    merged, method, W = G.cluster_from_device_pass(dp, W_override=g[f"{name}_W_all"])
+    merged, method, W = G.cluster_from_device_pass(dp, W_override=g[f"{name}_W_all"],
+                                                  block_sums=lambda groups: go.block_sums_ref(dp.sim_sharp, groups))
     assert method == meta[f"{name}_scalars"]["method_used"]
     n = dp.sim_sharp.shape[0]
     sentences = [f"s{i}" for i in range(n)]
@@ -98,7 +99,8 @@ def test_host_stage_matches_live_reference_on_random_documents():
                           q80=thr["edge_floor"], q65=thr["tau_merge"], q60=thr["global_merge_thr"],
                           reassign_delta=thr["reassign_delta"], n_positive=thr["count"], k_all=res["k_eff_all"],
                           knn_idx=kidx, knn_val=kval)
-        merged, method, _W = G.cluster_from_device_pass(dp, W_override=np.asarray(loc["W_all"]))
+        merged, method, _W = G.cluster_from_device_pass(dp, W_override=np.asarray(loc["W_all"]),
+                                                       block_sums=lambda groups, _s=res["sim_sharp"]: go.block_sums_ref(_s, groups))
         assert method == str(loc["method_used"])
         chunks = G._emit(f"doc_hg{trial}", text, sents, merged, method, dp, collect_metadata=True)
         assert [c[0] for c in chunks] == [w[0] for w in want], trial
@@ -106,3 +108,35 @@ def test_host_stage_matches_live_reference_on_random_documents():
             assert json.loads(mj) == json.loads(wj), cid
         checked += 1
     assert checked >= 4
+
+
+def test_host_stage_refuses_to_run_without_device_block_sums(golden_dir):
+    """The product path has no host fallback for the block means: a DevicePass without its device callable raises."""
+    g = np.load(os.path.join(golden_dir, "grouping.npz"))
+    meta = json.loads(str(g["meta_json"]))
+    dp = _device_pass_from_golden(g, meta, "a")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.cluster_from_device_pass(dp, W_override=g["a_W_all"])
+
+
+def test_block_sums_oracle_equals_the_reference_loops():
+    """oracle.block_sums_ref against the reference's element-by-element `_mean_between` / `_mean_within` definitions
+    (Grouping:118-130), including a repeated member."""
+    rng = np.random.default_rng(3)
+    A = rng.random((20, 20)).astype(np.float32)
+    sharp = np.maximum(A, A.T)
+    np.fill_diagonal(sharp, 0.0)
+    groups = [[0, 3, 5], [1, 2, 2, 7], [9], []]
+    rowsum, block = go.block_sums_ref(sharp, groups)
+    gm = G._GroupMeans(lambda gs: go.block_sums_ref(sharp, gs), groups)
+    for a, ga in enumerate(groups):
+        for b, gb in enumerate(groups):
+            want = float(np.mean([float(sharp[i, j]) for i in ga for j in gb])) if ga and gb else 0.0
+            assert abs(gm.between([a], [b]) - want) < 1e-12
+        vals = [float(sharp[ga[i], ga[j]]) for i in range(len(ga)) for j in range(i + 1, len(ga))]
+        want_w = float(np.mean(vals)) if len(ga) > 1 and vals else 1.0
+        assert abs(gm.within([a]) - want_w) < 1e-12
+    u = sorted(groups[0] + groups[1])
+    vals = [float(sharp[u[i], u[j]]) for i in range(len(u)) for j in range(i + 1, len(u))]
+    assert abs(gm.within([0, 1]) - float(np.mean(vals))) < 1e-12
+    assert rowsum.shape == (20, 4) and block.shape == (4, 4)
