@@ -60,6 +60,8 @@ struct GemmParams {
   const float* inv_gmax;  // [n_fill / 32] largest 1/|c| of each 32-row group (NaN rows ignored)
   const float* inv_q;
   uint64_t* gtop;  // [n_queries][k] global best-first key list of every query, zeroed before launch (see publish_list)
+  int* progress;   // [gridDim.x] units started by every CTA's producer, zeroed before launch (drift throttle); may be null
+  int max_lead;    // a producer starts its j-th unit only when the slowest CTA has started its (j - max_lead)-th
 };
 
 // Per-thread top-k list in shared memory, entry j of epilogue thread e at list[j * 128 + e]
@@ -175,10 +177,26 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0, ia = 0;
+    {
+      int s = 0, ia = 0, j_unit = 0;
       uint32_t ph = 0, ia_ph = 0;
       for (long long u = worker; u < p.n_units; u += n_workers) {
+        // Drift throttle.  The query blocks that share a corpus chunk run on different CTAs at about the same time and
+        // meet in L2; with a static unit list nothing keeps them together for thousands of units, and a CTA that runs
+        // ahead re-reads from DRAM what the others will fetch again later.  Every producer counts the units it has
+        // started; nobody starts unit j before the slowest CTA has started unit j - max_lead (the slowest never waits).
+        if (p.progress != nullptr) {
+          ++j_unit;
+          if (lane == 0) *reinterpret_cast<volatile int*>(p.progress + blockIdx.x) = j_unit;
+          for (;;) {
+            int mn = 0x7fffffff;
+            for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) mn = min(mn, *reinterpret_cast<volatile int*>(p.progress + i));
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            if (j_unit - mn <= p.max_lead) break;
+            __nanosleep(500);
+          }
+        }
+        if (lane != 0) continue;
         const int chunk = static_cast<int>(u / p.n_qb), qb = static_cast<int>(u % p.n_qb) * CG + static_cast<int>(cta_rank);
         const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
         const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
@@ -214,6 +232,8 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           }
         }
       }
+      // a CTA that has issued its last load holds nobody back
+      if (p.progress != nullptr && lane == 0) *reinterpret_cast<volatile int*>(p.progress + blockIdx.x) = 0x7fffffff;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader only when CG = 2) =====================
@@ -472,7 +492,7 @@ extern "C" size_t ss_cosine_topk_gemm_workspace_bytes(int64_t n_rows, int dim, i
   const GemmPlan g = make_gemm_plan(n_rows, n_queries);
   (void)g;
   return align_up(static_cast<size_t>(n_rows), G_BN) * 4 + align_up(align_up(static_cast<size_t>(n_rows), G_BN) / 32 * 4, 256) +
-         align_up(static_cast<size_t>(n_queries) * 4, 256) + align_up(static_cast<size_t>(n_queries) * k * 8, 256) + 256;
+         align_up(static_cast<size_t>(n_queries) * 4, 256) + align_up(static_cast<size_t>(n_queries) * k * 8, 256) + 4096 + 256;
 }
 
 // corpus_norms_valid: the head of `workspace` (inverse norms of the corpus rows and their 32-row group maxima, whose
@@ -502,7 +522,9 @@ static int cosine_topk_gemm_impl(const void* corpus, int64_t n_rows, int dim, in
   float* inv_q = reinterpret_cast<float*>(ws);
   ws += align_up(static_cast<size_t>(n_queries) * 4, 256);
   uint64_t* gtop = reinterpret_cast<uint64_t*>(ws);
-  SS_CUDA_CHECK(cudaMemsetAsync(gtop, 0, static_cast<size_t>(n_queries) * k * 8, st));
+  const size_t gtop_bytes = align_up(static_cast<size_t>(n_queries) * k * 8, 256);
+  int* progress = reinterpret_cast<int*>(ws + gtop_bytes);  // 1024 ints: one per CTA of the grid (<= 2 * workers)
+  SS_CUDA_CHECK(cudaMemsetAsync(gtop, 0, gtop_bytes + 4096, st));
 
   cudaError_t e = cudaSuccess;
   if (dtype == SS_BF16) {
@@ -541,6 +563,9 @@ static int cosine_topk_gemm_impl(const void* corpus, int64_t n_rows, int dim, in
   p.inv_gmax = inv_gmax;
   p.inv_q = inv_q;
   p.gtop = gtop;
+  static const int max_lead = getenv("SS_GEMM_MAX_LEAD") ? atoi(getenv("SS_GEMM_MAX_LEAD")) : 2;
+  p.max_lead = max_lead;
+  p.progress = (max_lead > 0 && sm_count() <= 1024) ? progress : nullptr;
   const uint32_t idesc = make_idesc(dtype == SS_BF16 ? 1 : 0, G_BM * cg, G_BN);
   const size_t per_stage = cg == 2 ? GemmCfg<2>::kStageBytes : GemmCfg<1>::kStageBytes;
   const size_t fixed = 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * G_BN * 4 + 2 * (G_BN / 32) * 4 + static_cast<size_t>(k) * G_EPI_THREADS * sizeof(ScoreIdx);
