@@ -45,12 +45,17 @@ def parse_args():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
                     help="corpus/query storage type (BASELINE config 4: bf16; config 5: fp16 with --rows 100000000 --dim 384 --k 100 --batch 16)")
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
-    ap.add_argument("--cpu-sample-queries", type=int, default=8)
+    ap.add_argument("--cpu-sample-queries", type=int, default=2)
+    ap.add_argument("--no-anchor", action="store_true",
+                    help="reference arm: skip the un-extrapolated anchor (1 query over the full fp32 corpus, needs ~3x its bytes of host RAM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
                     help="multi-GPU exchange of the per-GPU top-k keys: NCCL all-gather + merge, or the fused NVLink peer-memory push + merge")
     ap.add_argument("--graphs", default="on", choices=["on", "off"],
                     help="replay the search (local kernels + all-gather + merge) as one CUDA graph in the timed loops")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra.cfg1 / cfg2 / cfg3 / cfg5_shard / c99_* / rank_groups entries (single-GPU default run only)")
+    ap.add_argument("--extras", default="", help="comma-separated subset of the extra entries to run")
     ap.add_argument("--algo", default="auto", choices=["auto", "stream", "tcstream", "gemm"],
                     help="force one kernel for the headline batch (experiments); auto = the library's dispatch")
     return ap.parse_args()
@@ -71,10 +76,32 @@ def peaks():
 # --------------------------------------------------------------------------------------------
 # CPU baseline: the reference's own expression, timed on the host cores of this box
 # --------------------------------------------------------------------------------------------
+def _sample_inputs(args, rows, nq):
+    """The GPU arm's value distribution: N(0,1) rounded to the storage type (bf16 / fp16), upcast to fp32 for numpy."""
+    import numpy as np
+    import torch
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    g = torch.Generator().manual_seed(6)
+    C = torch.empty((rows, args.dim), dtype=torch.float32)
+    for a in range(0, rows, 1 << 18):
+        b = min(rows, a + (1 << 18))
+        C[a:b] = torch.randn((b - a, args.dim), generator=g).to(dt).float()
+    Q = torch.randn((nq, args.dim), generator=torch.Generator().manual_seed(7)).to(dt).float()
+    return C.numpy(), Q.numpy()
+
+
+def _cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_qps(args, steps=1, warmup=0):
-    """Times cosine_similarity(q.reshape(1,-1), C)[0] + np.argsort(-s)[:k] per query — the exact
-    expression at Tool/rank_chunks_optimized.py:215-216,225 — on a bounded sample of the
-    workload (fp32 upcast of bf16-rounded N(0,1) rows), scaled linearly to the full corpus."""
+    """Times cosine_similarity(q.reshape(1,-1), C)[0] + np.argsort(-s)[:k] per query — the exact expression at
+    Tool/rank_chunks_optimized.py:215-216,225 — with all the host threads BLAS takes.  One step = one pass of
+    `cpu_sample_queries` queries over a `cpu_sample_rows`-row sample of the corpus (same storage-rounded values as the GPU
+    arm); the full-corpus figure is that rate scaled by rows / sample rows and is flagged as extrapolated."""
     import numpy as np
     try:
         from sklearn.metrics.pairwise import cosine_similarity  # the reference's call (rank:15)
@@ -84,9 +111,8 @@ def cpu_reference_qps(args, steps=1, warmup=0):
         how = "oracle.cosine_similarity_ref+np.argsort"
     rows = min(args.cpu_sample_rows, args.rows)
     nq = args.cpu_sample_queries
-    rng = np.random.default_rng(6)
-    C = rng.standard_normal((rows, args.dim), dtype=np.float32)
-    Q = np.random.default_rng(7).standard_normal((nq, args.dim), dtype=np.float32)
+    C, Q = _sample_inputs(args, rows, nq)
+
     def one_pass():
         for b in range(nq):
             s = cosine_similarity(Q[b].reshape(1, -1), C)[0]
@@ -97,42 +123,74 @@ def cpu_reference_qps(args, steps=1, warmup=0):
     for _ in range(max(1, steps)):
         one_pass()
     dt = (time.perf_counter() - t0) / max(1, steps)
-    qps_sample = nq / dt
-    qps_full = qps_sample * rows / args.rows
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        cores = os.cpu_count() or 1
+    qps_full = (nq / dt) * rows / args.rows
     return {
-        "value": qps_full, "unit": UNIT, "cores": cores, "kind": "port",
+        "value": qps_full, "unit": UNIT, "cores": _cores(), "kind": "port", "extrapolated": rows != args.rows,
+        "sample_factor": rows / args.rows, "sample_seconds_per_step": dt, "how": how,
         "sample": (f"{how}, one call per query as in rank_chunks_optimized.py:215-216,225; {nq} queries x {rows} "
-                   f"rows x {args.dim} fp32 in {dt:.2f}s, scaled x{rows / args.rows:.3g} to {args.rows} rows (extrapolated)"),
+                   f"rows x {args.dim} ({args.dtype}-rounded values as fp32) per step, {dt:.2f}s per step, scaled x{rows / args.rows:.3g} "
+                   f"to {args.rows} rows"),
     }, dt
+
+
+def cpu_reference_anchor(args):
+    """One UN-extrapolated point: one query over the whole corpus as fp32 (what the reference would hold in RAM).  The
+    corpus is a 1 M-row storage-rounded block tiled to the full row count (timing does not depend on the values)."""
+    import numpy as np
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    need = 3.2 * args.rows * args.dim * 4   # the corpus, sklearn's normalised copy, slack
+    if avail < need:
+        return {"skipped": f"needs {need / 1e9:.0f} GB of host RAM, {avail / 1e9:.0f} GB available"}
+    from sklearn.metrics.pairwise import cosine_similarity
+    block, Q = _sample_inputs(args, min(args.rows, 1_000_000), 1)
+    C = np.empty((args.rows, args.dim), dtype=np.float32)
+    for a in range(0, args.rows, block.shape[0]):
+        b = min(args.rows, a + block.shape[0])
+        C[a:b] = block[: b - a]
+    t0 = time.perf_counter()
+    s = cosine_similarity(Q[0].reshape(1, -1), C)[0]
+    top = np.argsort(-s)[: args.k]
+    dt = time.perf_counter() - t0
+    return {"queries": 1, "rows": int(args.rows), "seconds": dt, "value": 1.0 / dt, "unit": UNIT, "extrapolated": False,
+            "cores": _cores(), "top1_row": int(top[0])}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, dt = cpu_reference_qps(args, steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup > 0 else 0)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    base, dt = cpu_reference_qps(args, steps=steps, warmup=warmup)
     line = {
         "impl": "reference", "metric": metric_name(args), "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "step_is": f"one pass of {args.cpu_sample_queries} queries over a {min(args.cpu_sample_rows, args.rows)}-row sample "
+                   "(NOT a full query batch over the full corpus: see extrapolated / sample_factor)",
+        "extrapolated": base["extrapolated"], "sample_factor": base["sample_factor"],
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_anchor:
+        try:
+            line["anchor"] = cpu_reference_anchor(args)
+        except MemoryError as exc:
+            line["anchor"] = {"skipped": f"MemoryError: {exc}"}
     emit(line)
 
 
 # DRAM traffic per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
 # `ncu --set full` captures committed under profiles/ — valid for exactly these single-GPU shapes.
 NCU_TRAFFIC = {
-    # K2 re-reads corpus tiles that fell out of L2 between the 16 query-block pairs of a chunk: 42.7 GB in the
-    # v4 capture, 98.7 GB in the final one (L2 hit 87 % / 76 %) against 15.4 GB of corpus — DRAM stays < 30 % busy
-    ("gemm", 10_000_000, 768, 4096): (98.708947e9 + 30.3e6, "profiles/r01_k2_final_ncu_summary.txt"),
+    # K2 with the drift throttle: the query blocks that share a corpus chunk stay inside an L2-sized window, the corpus
+    # streams from DRAM once (round 1: 98.7 GB, the blocks drifted apart)
+    ("gemm", 10_000_000, 768, 4096): (15.51e9 + 21.0e6, "profiles/r02_k2_final_ncu_summary.txt"),
     ("stream", 10_000_000, 768, 1): (15.360230e9 + 3.9e6, "profiles/r01_k1_final_ncu_summary.txt"),
     ("tcstream", 12_500_000, 384, 16): (9.601385e9 + 5.5e6, "profiles/r01_k7_cfg5_ncu_summary.txt"),
 }
@@ -225,6 +283,60 @@ def make_shard(rows, dim, seed, device, dtype):
         b = min(rows, a + step)
         out[a:b] = torch.randn((b - a, dim), generator=g, device=device, dtype=torch.float32).to(dtype)
     return out
+
+
+def verify_search(corpus, q_dev, k, shard, lo, world, dev, n_check=8, tol=2e-3, tie_tol=1e-5):
+    """Result check inside the bench: (1) every rank must hold the same answer (hash of the returned indices, agreed with
+    an all-gather); (2) the first `n_check` queries are re-ranked exhaustively with a chunked torch fp32 matmul over the
+    rank's whole shard (upcast storage values, normalise, dot — the reference's arithmetic), the per-rank top-k are
+    all-gathered and merged, and the search result must equal that exact answer: scores within `tol`, indices identical
+    except where the exact scores of the swapped rows tie within `tie_tol`."""
+    import torch
+    import torch.distributed as dist
+    s, i = corpus.search(q_dev, k)
+    torch.cuda.synchronize()
+    mult = torch.arange(1, i.numel() + 1, device=dev, dtype=torch.int64).view_as(i)
+    h = ((i * mult) % 2147483647).sum().view(1)
+    hashes = [h.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(hashes, h)
+    hash_agree = all(int(x.item()) == int(h.item()) for x in hashes)
+    nq = min(n_check, q_dev.shape[0])
+    q = q_dev[:nq].float()
+    q = q / q.norm(dim=1, keepdim=True).clamp_min(1e-30)
+    best_s = torch.full((nq, k), -float("inf"), device=dev)
+    best_i = torch.full((nq, k), -1, dtype=torch.int64, device=dev)
+    step = 1 << 20
+    for a in range(0, shard.shape[0], step):
+        c = shard[a:a + step].float()
+        nrm = c.norm(dim=1, keepdim=True)
+        c = c / torch.where(nrm == 0, torch.ones_like(nrm), nrm)          # sklearn: zero rows divide by 1
+        sc = q @ c.T
+        kk = min(k, sc.shape[1])
+        ts, ti = torch.topk(sc, kk, dim=1)
+        cat_s = torch.cat([best_s, ts], dim=1)
+        cat_i = torch.cat([best_i, ti + (lo + a)], dim=1)
+        order = torch.argsort(cat_s, dim=1, descending=True, stable=True)[:, :k]
+        best_s, best_i = torch.gather(cat_s, 1, order), torch.gather(cat_i, 1, order)
+    if world > 1:
+        all_s = [torch.empty_like(best_s) for _ in range(world)]
+        all_i = [torch.empty_like(best_i) for _ in range(world)]
+        dist.all_gather(all_s, best_s)
+        dist.all_gather(all_i, best_i)
+        cat_s, cat_i = torch.cat(all_s, dim=1), torch.cat(all_i, dim=1)
+        order = torch.argsort(cat_s, dim=1, descending=True, stable=True)[:, :k]
+        best_s, best_i = torch.gather(cat_s, 1, order), torch.gather(cat_i, 1, order)
+    got_s, got_i = s[:nq], i[:nq]
+    score_err = float((got_s - best_s).abs().max().item())
+    diff = got_i != best_i
+    # a differing index is excused when the exact scores at that rank agree within tie_tol (the reference's argsort is
+    # not stable either); what must never happen is a returned row whose exact score is below the exact k-th best
+    bad = int((diff & ((got_s - best_s).abs() > max(tol, tie_tol))).sum().item())
+    kth_ok = bool((got_s[:, -1] >= best_s[:, -1] - tol).all().item())
+    return {"queries_checked": nq, "oracle": "chunked torch fp32 normalise + matmul over every shard, merged across ranks",
+            "max_score_err": score_err, "score_tol": tol, "index_mismatches": int(diff.sum().item()),
+            "index_mismatches_outside_tolerance": bad, "kth_score_ok": kth_ok, "ranks_agree": hash_agree,
+            "result_hash": int(h.item()), "ok": bool(hash_agree and bad == 0 and kth_ok and score_err <= tol)}
 
 
 def run_ours(args):
@@ -393,6 +505,7 @@ def run_ours(args):
         cur_algo[0] = main_algo
     total_ms, kern_ms, e2e_ms, clocks = measure(args.batch, args.steps, args.warmup)
     main_res = describe(args.batch, args.steps, total_ms, kern_ms, e2e_ms) if rank == 0 else None
+    verified = verify_search(corpus, q_dev, args.k, shard, lo, world, dev)
 
     if rank == 0:
         line = {
@@ -402,10 +515,22 @@ def run_ours(args):
             "config": workload_config(args), "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
             "roofline": main_res["roofline"], "clocks": clocks,
         }
-        if extra:
-            line["extra"] = extra
+        line["verified"] = verified
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_reference_qps(args)
+        default_shape = (args.rows, args.dim, args.k, args.dtype, args.batch) == (10_000_000, 768, 10, "bf16", 4096)
+        if world == 1 and not args.no_extras and (default_shape or args.extras):
+            # BASELINE.json's other configs and the two 8f legs, each with value / roofline / cpu_baseline / e2e
+            del corpus, shard
+            graphed[0] = None
+            q_dev = q_host = None
+            torch.cuda.empty_cache()
+            from benchmarks import extras as _extras
+            names = [n for n in args.extras.split(",") if n] or None
+            more = _extras.run_all(names, cpu=not args.no_cpu_baseline, log=lambda m: print(m, file=sys.stderr))
+            extra = dict(extra or {}, **more)
+        if extra:
+            line["extra"] = extra
         emit(line)
     if world > 1:
         if peer is not None:

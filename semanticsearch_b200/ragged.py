@@ -402,3 +402,143 @@ def knn_graph_from_lists(knn_idx: np.ndarray, knn_val: np.ndarray, floor: float)
     keep = (cols >= 0) & (cols != rows) & (vals >= floor)
     W[rows[keep], cols[keep]] = vals[keep]
     return np.maximum(W, W.T)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Host-buffer operators: the calls a pipeline makes when its embeddings sit in host memory (the reference's
+# numpy arrays).  Inputs are host tensors (pinned memory makes the copies asynchronous), outputs are pinned host
+# tensors; every function raises without a CUDA device.
+# ----------------------------------------------------------------------------------------------------------------
+def _pinned_like(t: torch.Tensor) -> torch.Tensor:
+    return torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+
+
+def _to_host(tensors: Dict[str, torch.Tensor], out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    host = out if out is not None else {k: _pinned_like(v) for k, v in tensors.items()}
+    for k, v in tensors.items():
+        host[k].copy_(v, non_blocking=True)
+    return host
+
+
+def grouping_pass_host(E_host: torch.Tensor, sizes: Sequence[int], tau: float = 0.15, knn_mode: int = 0,
+                       out: Optional[Dict[str, torch.Tensor]] = None, plan: Optional[RaggedPlan] = None) -> Dict[str, torch.Tensor]:
+    """``create_similarity_matrix`` + the grouping threshold pass (Method/semantic_common.py:158-191,
+    Method/Semantic_Grouping_Optimized.py:100-115,270-283,351-355) for a packed batch of documents whose embeddings are
+    in HOST memory: H2D copy, K3, K4, D2H copy of everything the host clustering stage reads (S, sim_sharp,
+    centrality, per-document thresholds, neighbour lists).  ``out``: the dict a previous call returned, to reuse its
+    pinned buffers.  The call synchronises before returning (the caller reads the results)."""
+    if E_host.is_cuda:
+        raise ValueError("grouping_pass_host takes host embeddings (use segmented_simmatrix / group_threshold_pass for device tensors)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    plan = plan or make_plan(sizes, dev)
+    E = E_host.to(dev, non_blocking=True)
+    S = segmented_simmatrix(E, plan)
+    res = group_threshold_pass(S, plan, tau=tau, knn_mode=knn_mode)
+    res["S"] = S
+    host = _to_host(res, out)
+    torch.cuda.current_stream(dev).synchronize()
+    return host
+
+
+def splitter_breakpoints_host(E_host: torch.Tensor, sizes: Sequence[int], pct: float = 95.0, want_stats: bool = False,
+                              out: Optional[Dict[str, torch.Tensor]] = None, plan: Optional[RaggedPlan] = None) -> Dict[str, torch.Tensor]:
+    """Adjacent-sentence cosine + per-document percentile breakpoints (Method/Semantic_Splitter_Optimized.py:140-152,412;
+    BASELINE.json config 3) for a packed batch of documents in HOST memory: H2D, K5a, K5b, D2H of ``adj`` (fp32 per row),
+    ``thr`` (fp64 per document) and ``flags`` (u8 per row)."""
+    if E_host.is_cuda:
+        raise ValueError("splitter_breakpoints_host takes host embeddings")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    plan = plan or make_plan(sizes, dev)
+    E = E_host.to(dev, non_blocking=True)
+    adj = adjacent_cosine(E)
+    thr, flags, stats, smooth = segmented_percentile(adj, plan, pct, want_stats=want_stats)
+    res = {"adj": adj, "thr": thr, "flags": flags}
+    if want_stats:
+        res.update({"stats": stats, "smooth": smooth})
+    host = _to_host(res, out)
+    torch.cuda.current_stream(dev).synchronize()
+    return host
+
+
+class SplitterStream:
+    """Config 3 at corpus scale: batches of documents stream from pinned HOST memory through a double-buffered
+    H2D -> K5a -> K5b -> D2H pipeline (copy engine and SMs overlap; two device buffers, two result buffers).  A corpus of
+    1 M documents x 384 fp32 is 405 GB: it never fits the device, and the pipeline is bound by the host link.
+
+        stream = SplitterStream(max_rows, dim, max_docs)
+        for E_host_pinned, sizes in batches:
+            prev = stream.submit(E_host_pinned, sizes)      # results of the batch submitted two calls ago, or None
+        for res in stream.drain(): ...
+    """
+
+    def __init__(self, max_rows: int, dim: int, max_docs: int, pct: float = 95.0, device=None):
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.pct = float(pct)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.slots = []
+        for _ in range(2):
+            self.slots.append({
+                "E": torch.empty((max_rows, dim), dtype=torch.float32, device=self.dev),
+                "adj": torch.empty(max_rows, dtype=torch.float32, device=self.dev),
+                "h_thr": torch.empty(max_docs, dtype=torch.float64, pin_memory=True),
+                "h_flags": torch.empty(max_rows, dtype=torch.uint8, pin_memory=True),
+                "copied": torch.cuda.Event(), "computed": torch.cuda.Event(), "done": torch.cuda.Event(),
+                "busy": False, "plan": None, "rows": 0,
+            })
+        self.turn = 0
+
+    def _finish(self, slot):
+        slot["done"].synchronize()
+        slot["busy"] = False
+        plan = slot["plan"]
+        return {"thr": slot["h_thr"][: plan.n_docs], "flags": slot["h_flags"][: slot["rows"]], "plan": plan}
+
+    def submit(self, E_host: torch.Tensor, sizes: Sequence[int], plan: Optional[RaggedPlan] = None):
+        slot = self.slots[self.turn]
+        self.turn ^= 1
+        ready = self._finish(slot) if slot["busy"] else None
+        plan = plan or make_plan(sizes, self.dev)
+        rows = plan.total_rows
+        if rows > slot["E"].shape[0] or plan.n_docs > slot["h_thr"].numel():
+            raise ValueError("batch larger than the stream's buffers")
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot["computed"])          # the kernels that read this buffer last time are done
+            slot["E"][:rows].copy_(E_host[:rows], non_blocking=True)
+            slot["copied"].record(self.copy_stream)
+        main.wait_event(slot["copied"])
+        adjacent_cosine(slot["E"][:rows], out=slot["adj"][:rows])
+        thr, flags, _, _ = segmented_percentile(slot["adj"][:rows], plan, self.pct, want_stats=False)
+        slot["computed"].record(main)
+        slot["h_thr"][: plan.n_docs].copy_(thr, non_blocking=True)
+        slot["h_flags"][:rows].copy_(flags, non_blocking=True)
+        slot["done"].record(main)
+        slot.update(busy=True, plan=plan, rows=rows)
+        return ready
+
+    def drain(self):
+        out = []
+        for _ in range(2):
+            slot = self.slots[self.turn]
+            self.turn ^= 1
+            if slot["busy"]:
+                out.append(self._finish(slot))
+        return out
+
+
+def c99_cuts_host(E_host: torch.Tensor, sizes: Sequence[int], min_chunk, use_local_rank: bool = False, mask_size: int = 11,
+                  min_gain: float = 0.01, plan: Optional[RaggedPlan] = None) -> Dict[str, torch.Tensor]:
+    """The C99 leg of the splitter (Method/Semantic_Splitter_Optimized.py:169-238) for a packed batch of documents in
+    HOST memory: H2D, similarity matrices, rank transform (global, or the reference preset's 11 x 11 local rank,
+    data_process/simple_chunk_controller.py:1451), divisive cut search, D2H of the cuts."""
+    if E_host.is_cuda:
+        raise ValueError("c99_cuts_host takes host embeddings")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    plan = plan or make_plan(sizes, dev)
+    E = E_host.to(dev, non_blocking=True)
+    S = segmented_simmatrix(E, plan)
+    R = c99_rank_matrix(S, plan, use_local_rank=use_local_rank, mask_size=mask_size, symmetric=not use_local_rank)
+    cuts, n_cuts, _ = c99_divisive_cuts(R, plan, min_chunk, min_gain=min_gain)
+    host = _to_host({"cuts": cuts, "n_cuts": n_cuts})
+    torch.cuda.current_stream(dev).synchronize()
+    return host
