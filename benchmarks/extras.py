@@ -105,7 +105,7 @@ def cfg2(steps=3, docs=10000, cpu=True, traffic=None):
     plan = ragged.make_plan(sizes, "cuda")
     S = torch.empty(plan.total_s, dtype=torch.float32, device="cuda")
     ms_sim = cuda_time(lambda: ragged.segmented_simmatrix(E, plan, out=S), steps)
-    ms_grp = cuda_time(lambda: ragged.group_threshold_pass(S, plan), steps, warmup=1)
+    ms_grp = cuda_time(lambda: ragged.group_threshold_pass(S, plan, symmetric=True), steps, warmup=1)
     alg_sim = 4 * 768 * plan.total_rows + 4 * plan.total_s
     alg_grp = 8 * plan.total_s + plan.total_rows * (33 * 8 + 8)
     out = {"workload": f"cfg2: {docs} docs, n~U[16,512], 768-d fp32: S = En En^T + grouping threshold pass",

@@ -19,6 +19,6 @@ S = torch.empty(plan.total_s, dtype=torch.float32, device="cuda")
 for _ in range(a.iters):
     ragged.segmented_simmatrix(E, plan, out=S)
     if a.group:
-        ragged.group_threshold_pass(S, plan)
+        ragged.group_threshold_pass(S, plan, symmetric=True)
 torch.cuda.synchronize()
 print("ok", plan.total_rows, plan.total_s)

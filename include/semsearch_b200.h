@@ -205,9 +205,11 @@ int ss_segmented_simmatrix_tc(const float* rows, int64_t total_rows, int dim, co
  * filter and max-symmetrisation are applied by the caller).
  * out_doc_stats[d] = {mu, sigma, q80, q65, q60, 0.1*std(pos), count(pos), k}; out_knn_* are
  * [total_rows][33] (-1 / 0 padded).  knn_mode: 0 = auto k (:347), >0 = explicit knn_k (<= 32),
- * -1 = max(5, min(20, n-1)) (:349). */
+ * -1 = max(5, min(20, n-1)) (:349).  s_is_symmetric != 0 promises S == S^T bit for bit (true for the output of
+ * ss_segmented_simmatrix*): the order statistics and moments of the positive values are then taken over the strict
+ * upper triangle, which holds every value of the full multiset exactly once more. */
 int ss_group_threshold_pass(const float* S, const int32_t* offsets, const int64_t* s_offsets, int n_docs, float tau,
-                            int knn_mode, float* out_sharp, double* out_centrality, double* out_doc_stats,
+                            int knn_mode, int s_is_symmetric, float* out_sharp, double* out_centrality, double* out_doc_stats,
                             int32_t* out_knn_idx, float* out_knn_val, void* stream);
 
 /* ---- §8f-2: block sums of sim_sharp over cluster member lists, co-association of a label sweep ---------

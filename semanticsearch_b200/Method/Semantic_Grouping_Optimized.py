@@ -77,7 +77,7 @@ def device_pass_batch(doc_embeddings: Sequence[np.ndarray], tau: float = 0.15, k
     plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
     E = torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
     S = ragged.segmented_simmatrix(E, plan)
-    res = ragged.group_threshold_pass(S, plan, tau=tau, knn_mode=knn_mode)
+    res = ragged.group_threshold_pass(S, plan, tau=tau, knn_mode=knn_mode, symmetric=True)   # K3's S is bit-symmetric
     S_h = S.cpu().numpy()
     sharp_h = res["sim_sharp"].cpu().numpy()
     cent_h = res["centrality"].cpu().numpy()

@@ -34,6 +34,8 @@ struct GroupParams {
   int n_docs;
   float tau;
   int knn_mode;  // 0: auto k = clamp(round(0.06 n), 5, 32); >0: explicit k; -1: max(5, min(20, n-1))
+  int symmetric;  // caller promises S == S^T bit for bit (K3's output): order statistics and moments of the positive values
+                  // are taken over the strict upper triangle only (the full multiset is that one, twice)
   float* sharp;          // packed like S
   double* centrality;    // [total_rows]
   double* doc_stats;     // [n_docs][8]: mu, sigma, q80, q65, q60, 0.1*std(pos), count(pos), k_eff
@@ -159,11 +161,12 @@ struct RowCtx {
   float* knn_val;
 };
 
-// Monotone 2048-way binning of a sharpened value in (0, 1]: exact (power-of-two scale + truncation).
-__device__ __forceinline__ unsigned int lin_bin(float v) { return min(2047u, static_cast<unsigned int>(v * 2048.0f)); }
+// Monotone 2048-way binning of a sharpened value in [0, 1] (a multiply and a truncating conversion: 1.0f lands in bin 2047;
+// the selection only needs the map to be non-decreasing and identical in the histogram and the gather pass).
+__device__ __forceinline__ unsigned int lin_bin(float v) { return __float2uint_rz(v * 2047.9998f); }
 
 // One warp per row with the row held in NREG registers per lane (n <= 32 * NREG).
-template <int NREG, int kGrpWarps>
+template <int NREG, int kGrpWarps, bool SYM>
 __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int lane, double& pos_s1, double& pos_s2,
                                               unsigned int& pos_cnt) {
   const float* S = cx.S;
@@ -172,12 +175,12 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
   const float mu = cx.mu;
   const float zscale = 1.4426950408889634f / (cx.sigma * cx.tau);  // log2(e) / (sigma * tau)
   uint64_t* scr = cx.scr;
-  unsigned int c_lo = 0u, c_hi = 0u;  // this warp's counts of bins 0 and 2047, flushed once
+  unsigned int c_lo = 0u, c_hi = 0u;  // this LANE's counts of bins 0 and 2047 (the saturated ends of the sigmoid), flushed once
     for (int r = warp; r < n; r += kGrpWarps) {
       const float* srow = S + static_cast<size_t>(r) * n;
       float* orow = sharp + static_cast<size_t>(r) * n;
       uint32_t o[NREG];  // order-preserving bits of the sharpened value; 0 = column past the end
-      double rs = 0.0;
+      double rs = 0.0, ps1 = 0.0;
 #pragma unroll
       for (int j = 0; j < NREG; ++j) {  // the whole row in flight before any of it is consumed
         const int c = lane + 32 * j;
@@ -189,37 +192,37 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
         o[j] = 0u;
         if (32 * j < n) {
           const int c = lane + 32 * j;
-          bool pos = false;
-          unsigned int bits = 0u;
+          float v = 0.f;
           if (c < n) {
             // sigmoid(((S - mu) / sigma) / tau) with one FMA, ex2.approx and rcp.approx: a few ulp from
             // the reference's fp32 expression (Grouping:105-106), far inside the 1e-5 bound; saturates
             // to exactly 0 / 1 like numpy's exp overflow does
-            float e, v;
+            float e;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-((s_raw - mu) * zscale)));
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(1.0f + e));
             if (c == r) v = 0.f;
             orow[c] = v;
-            const double vd = static_cast<double>(v);  // float64 sums: 0.1 * std(vals) stays within 1e-9 of numpy's
-            rs += vd;                                   // zeros add nothing: also the sum of the positive values
-            pos_s2 = fma(vd, vd, pos_s2);
+            rs += static_cast<double>(v);
             o[j] = __float_as_uint(v) | 0x80000000u;    // float_to_ordered of a non-negative value
-            if (v > 0.f) {
-              pos = true;
-              bits = __float_as_uint(v);
+          }
+          // moments and histogram of the "positive values": with a symmetric S only the strict upper triangle is
+          // counted (register blocks left of the diagonal skip the work altogether, a warp-uniform test)
+          if (!SYM || 32 * j + 31 > r) {
+            const bool take = v > 0.f && (!SYM || c > r);   // v == 0 for columns past the end
+            if (take) {
+              const double vd = static_cast<double>(v);  // float64 sums: 0.1 * std(vals) stays within 1e-9 of numpy's
+              ps1 += vd;
+              pos_s2 = fma(vd, vd, pos_s2);
               ++pos_cnt;
             }
+            const unsigned int bin = lin_bin(v);
+            c_lo += (take && bin == 0u) ? 1u : 0u;
+            c_hi += (take && bin == 2047u) ? 1u : 0u;
+            if (take && bin - 1u < 2046u) atomicAdd(&cx.hist[bin], 1u);
           }
-          // histogram: the saturated ends of the sigmoid (bins 0 and 2047 hold a quarter of the values and more)
-          // are counted with ballots into warp-uniform registers; every other bin takes a plain shared-memory atomic
-          const unsigned int bin = lin_bin(__uint_as_float(bits));
-          const bool sat_lo = pos && bin == 0u, sat_hi = pos && bin == 2047u;
-          c_lo += __popc(__ballot_sync(0xffffffffu, sat_lo));
-          c_hi += __popc(__ballot_sync(0xffffffffu, sat_hi));
-          if (pos && !sat_lo && !sat_hi) atomicAdd(&cx.hist[bin], 1u);
         }
       }
-      pos_s1 += rs;
+      pos_s1 += ps1;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
       if (lane == 0) {
@@ -229,8 +232,6 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
       // top-`width` of the row (value desc, index asc).  Cheap bound first: each lane's two largest values
       // form a 64-value sample; its width-th largest L is a lower bound of the row's width-th largest, and
       // usually only a few more than `width` columns reach L — gather those and sort them.
-      scr[lane] = 0ull;
-      scr[lane + 32] = 0ull;
       const unsigned int lt_mask = (1u << lane) - 1u;
       uint32_t m1 = 0u, m2 = 0u;
 #pragma unroll
@@ -240,10 +241,52 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
       }
       warp_sort64_desc<uint32_t>(m1, m2, lane);  // width <= n real columns are in the sample, so L is a real value
       const uint32_t L = __shfl_sync(0xffffffffu, ((width - 1) & 1) ? m2 : m1, (width - 1) >> 1);
+      const uint32_t vmax = __shfl_sync(0xffffffffu, m1, 0);  // the row's largest value (sorted slot 0)
       int c_ge = 0;
 #pragma unroll
       for (int j = 0; j < NREG; ++j) c_ge += (o[j] >= L) ? 1 : 0;
       c_ge = __reduce_add_sync(0xffffffffu, c_ge);
+      int* oi = cx.knn_idx + static_cast<size_t>(row_base + r) * kKnnWidth;
+      float* ov = cx.knn_val + static_cast<size_t>(row_base + r) * kKnnWidth;
+      if (c_ge <= 64 && vmax - L < (1u << 26) - 1u) {
+        // Usual case: at most 64 candidates whose ordered bits span less than 2^26 above L.  The compaction below lists them in
+        // ascending column order, so (value - L) << 6 | (63 - position) is a 32-bit key with the order "value descending,
+        // column ascending": the final sort runs on 32-bit keys (half the shuffles and compares of the 64-bit network).
+        uint32_t* keys32 = reinterpret_cast<uint32_t*>(scr);
+        uint16_t* cols16 = reinterpret_cast<uint16_t*>(keys32 + 64);
+        scr[lane] = 0ull;  // keys32[2 * lane], keys32[2 * lane + 1]: 0 = empty slot, sorts last
+        __syncwarp();
+        int base = 0;
+#pragma unroll
+        for (int j = 0; j < NREG; ++j) {
+          if (32 * j < n) {
+            const unsigned int m_ge = __ballot_sync(0xffffffffu, o[j] >= L);
+            if (o[j] >= L) {
+              const int pos = base + __popc(m_ge & lt_mask);
+              keys32[pos] = (((o[j] - L) << 6) | static_cast<uint32_t>(63 - pos)) + 1u;
+              cols16[pos] = static_cast<uint16_t>(lane + 32 * j);
+            }
+            base += __popc(m_ge);
+          }
+        }
+        __syncwarp();
+        uint32_t k0 = keys32[2 * lane], k1 = keys32[2 * lane + 1];
+        warp_sort64_desc<uint32_t>(k0, k1, lane);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // lane holds sorted slots 2 * lane and 2 * lane + 1
+          const int sl = 2 * lane + h;
+          const uint32_t key = (h ? k1 : k0) - 1u;
+          if (sl < kKnnWidth) {
+            const bool ok = sl < width;  // c_ge >= width: the first `width` sorted slots are real candidates
+            oi[sl] = ok ? static_cast<int>(cols16[63 - (key & 63u)]) : -1;
+            ov[sl] = ok ? ordered_to_float(L + (key >> 6)) : 0.f;
+          }
+        }
+        __syncwarp();
+        continue;
+      }
+      scr[lane] = 0ull;
+      scr[lane + 32] = 0ull;
       __syncwarp();
       if (c_ge <= 64) {
         int base = 0;
@@ -292,20 +335,20 @@ __device__ __forceinline__ void row_pass_regs(const RowCtx& cx, int warp, int la
       __syncwarp();
       unsigned long long k0 = scr[2 * lane], k1 = scr[2 * lane + 1];
       warp_sort64_desc<unsigned long long>(k0, k1, lane);
-      int* oi = cx.knn_idx + static_cast<size_t>(row_base + r) * kKnnWidth;
-      float* ov = cx.knn_val + static_cast<size_t>(row_base + r) * kKnnWidth;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {  // lane holds sorted slots 2 * lane and 2 * lane + 1
-        const int s = 2 * lane + h;
+        const int sl = 2 * lane + h;
         const unsigned long long key = h ? k1 : k0;
-        if (s < kKnnWidth) {
-          const bool ok = s < width;
-          oi[s] = ok ? static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull)) : -1;
-          ov[s] = ok ? ordered_to_float(static_cast<uint32_t>(key >> 32)) : 0.f;
+        if (sl < kKnnWidth) {
+          const bool ok = sl < width;
+          oi[sl] = ok ? static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull)) : -1;
+          ov[sl] = ok ? ordered_to_float(static_cast<uint32_t>(key >> 32)) : 0.f;
         }
       }
       __syncwarp();
     }
+  c_lo = __reduce_add_sync(0xffffffffu, c_lo);
+  c_hi = __reduce_add_sync(0xffffffffu, c_hi);
   if (lane == 0) {
     if (c_lo) atomicAdd(&cx.hist[0], c_lo);
     if (c_hi) atomicAdd(&cx.hist[2047], c_hi);
@@ -484,7 +527,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) group_threshold_small_kernel
 // NT = 512 threads for documents of more than 128 sentences, 128 threads for 33..128: a mid-size document
 // keeps only a few warps busy, and every block barrier costs the idle ones.
 template <int NT>
-__global__ void __launch_bounds__(NT) group_threshold_kernel(const GroupParams p, int n_min, int n_max) {
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 5) group_threshold_kernel(const GroupParams p, int n_min, int n_max) {
   constexpr int kGrpThreads = NT;
   constexpr int kGrpWarps = NT / 32;
   __shared__ double red[kGrpWarps];
@@ -558,16 +601,26 @@ __global__ void __launch_bounds__(NT) group_threshold_kernel(const GroupParams p
   // ---- 2. sharpen, zero the diagonal, row sums, first radix histogram, kNN lists -----------------
   double pos_s1 = 0.0, pos_s2 = 0.0;
   unsigned int pos_cnt = 0;
+  // symmetric S on the register path: the histogram, the moments and the gather pass below see the strict upper triangle
+  // only; every count, sum and rank of the full multiset is twice / half of what they see
+  const bool sym = p.symmetric != 0 && n <= kFastMaxN;
   if (n <= kFastMaxN) {
     // Fast path: one warp per row, the row stays in registers for all four products of the pass.
     RowCtx cx;
     cx.S = S; cx.sharp = sharp; cx.n = n; cx.row_base = row_base; cx.width = width;
     cx.mu = mu; cx.sigma = sigma; cx.tau = tau; cx.hist = hist[0]; cx.scr = knn_scr[warp];
     cx.centrality = p.centrality; cx.knn_idx = p.knn_idx; cx.knn_val = p.knn_val;
-    if (n <= 128) row_pass_regs<4, kGrpWarps>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
-    else if (n <= 256) row_pass_regs<8, kGrpWarps>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
-    else if (n <= 384) row_pass_regs<12, kGrpWarps>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
-    else row_pass_regs<16, kGrpWarps>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    if (sym) {
+      if (n <= 128) row_pass_regs<4, kGrpWarps, true>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+      else if (n <= 256) row_pass_regs<8, kGrpWarps, true>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+      else if (n <= 384) row_pass_regs<12, kGrpWarps, true>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+      else row_pass_regs<16, kGrpWarps, true>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    } else {
+      if (n <= 128) row_pass_regs<4, kGrpWarps, false>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+      else if (n <= 256) row_pass_regs<8, kGrpWarps, false>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+      else if (n <= 384) row_pass_regs<12, kGrpWarps, false>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+      else row_pass_regs<16, kGrpWarps, false>(cx, warp, lane, pos_s1, pos_s2, pos_cnt);
+    }
   } else {
     // Generic path for very long documents: rows are re-read from memory.
     for (int r = warp; r < n; r += kGrpWarps) {
@@ -627,10 +680,11 @@ __global__ void __launch_bounds__(NT) group_threshold_kernel(const GroupParams p
       }
     }
   }
-  pos_s1 = block_sum<NT>(pos_s1, red);
-  pos_s2 = block_sum<NT>(pos_s2, red);
-  const double m_d = block_sum<NT>(static_cast<double>(pos_cnt), red);
+  pos_s1 = block_sum<NT>(pos_s1, red) * (sym ? 2.0 : 1.0);
+  pos_s2 = block_sum<NT>(pos_s2, red) * (sym ? 2.0 : 1.0);
+  const double m_d = block_sum<NT>(static_cast<double>(pos_cnt), red) * (sym ? 2.0 : 1.0);
   const unsigned int m = static_cast<unsigned int>(m_d + 0.5);
+  const int rsh = sym ? 1 : 0;  // rank r of the full multiset = rank r >> rsh of what the histogram counted
   __syncthreads();  // sharp[] and the pass-0 histogram written by this CTA are visible to the whole CTA
 
   // ---- 3. radix select of the lower order statistic of each quantile ---------------------------
@@ -649,7 +703,7 @@ __global__ void __launch_bounds__(NT) group_threshold_kernel(const GroupParams p
     // 3a. walk the linear-bin histogram: bin, rank inside the bin and population of the bin per target
     if (warp < kNumQ) {
       unsigned int bin, rin, cnt;
-      walk_hist(hist[0], kRadixBins, lo_rank[warp], lane, bin, rin, cnt);
+      walk_hist(hist[0], kRadixBins, lo_rank[warp] >> rsh, lane, bin, rin, cnt);
       if (lane == 0) {
         t_prefix[warp] = bin;
         t_rank[warp] = rin;
@@ -668,21 +722,38 @@ __global__ void __launch_bounds__(NT) group_threshold_kernel(const GroupParams p
       if (tid < kNumQ) t_fill[tid] = 0u;
       __syncthreads();
       unsigned int a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
-      for (long long i0 = 0; i0 < nn; i0 += 8 * kGrpThreads) {
-        unsigned int bb[8];
+      auto visit = [&](unsigned int b) {
+        if (b == 0u) return;  // diagonal / underflowed zeros are not "positive values"
+        const unsigned int bin = lin_bin(__uint_as_float(b));
+        if (bin == b0) lists[atomicAdd(&t_fill[0], 1u)] = b; else if (bin > b0) a0 = min(a0, b);
+        if (bin == b1) lists[kListCap + atomicAdd(&t_fill[1], 1u)] = b; else if (bin > b1) a1 = min(a1, b);
+        if (bin == b2) lists[2 * kListCap + atomicAdd(&t_fill[2], 1u)] = b; else if (bin > b2) a2 = min(a2, b);
+      };
+      if (sym) {
+        // strict upper triangle, one warp per row, four independent loads per lane and step
+        for (int r = warp; r < n - 1; r += kGrpWarps) {
+          const float* row = sharp + static_cast<size_t>(r) * n;
+          for (int c0 = r + 1; c0 < n; c0 += 128) {
+            unsigned int bb[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const long long i = i0 + q * kGrpThreads + tid;
-          bb[q] = i < nn ? __float_as_uint(sharp[i]) : 0u;
+            for (int q = 0; q < 4; ++q) {
+              const int c = c0 + q * 32 + lane;
+              bb[q] = c < n ? __float_as_uint(row[c]) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) visit(bb[q]);
+          }
         }
+      } else {
+        for (long long i0 = 0; i0 < nn; i0 += 8 * kGrpThreads) {
+          unsigned int bb[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const unsigned int b = bb[q];
-          if (b == 0u) continue;  // diagonal / underflowed zeros are not "positive values"
-          const unsigned int bin = lin_bin(__uint_as_float(b));
-          if (bin == b0) lists[atomicAdd(&t_fill[0], 1u)] = b; else if (bin > b0) a0 = min(a0, b);
-          if (bin == b1) lists[kListCap + atomicAdd(&t_fill[1], 1u)] = b; else if (bin > b1) a1 = min(a1, b);
-          if (bin == b2) lists[2 * kListCap + atomicAdd(&t_fill[2], 1u)] = b; else if (bin > b2) a2 = min(a2, b);
+          for (int q = 0; q < 8; ++q) {
+            const long long i = i0 + q * kGrpThreads + tid;
+            bb[q] = i < nn ? __float_as_uint(sharp[i]) : 0u;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) visit(bb[q]);
         }
       }
       a0 = __reduce_min_sync(0xffffffffu, a0);
@@ -707,7 +778,8 @@ __global__ void __launch_bounds__(NT) group_threshold_kernel(const GroupParams p
         const unsigned int rin = t_rank[t];
         const unsigned int vlo = l[rin];
         unsigned int vhi = vlo;
-        if (lo_rank[t] + 1 < m) vhi = (rin + 1 < cnt) ? l[rin + 1] : t_min_above[t];
+        // order statistic lo + 1 of the full multiset: the same counted value when both fall on one of its two copies
+        if (lo_rank[t] + 1 < m && ((lo_rank[t] + 1) >> rsh) != (lo_rank[t] >> rsh)) vhi = (rin + 1 < cnt) ? l[rin + 1] : t_min_above[t];
         q_out[t] = np_lerp(static_cast<double>(__uint_as_float(vlo)), static_cast<double>(__uint_as_float(vhi)), gamma[t]);
       }
     } else {
@@ -809,8 +881,8 @@ __global__ void __launch_bounds__(NT) group_threshold_kernel(const GroupParams p
 using namespace ss;
 
 extern "C" int ss_group_threshold_pass(const float* S, const int32_t* offsets, const int64_t* s_offsets, int n_docs, float tau,
-                                       int knn_mode, float* out_sharp, double* out_centrality, double* out_doc_stats,
-                                       int32_t* out_knn_idx, float* out_knn_val, void* stream) {
+                                       int knn_mode, int s_is_symmetric, float* out_sharp, double* out_centrality,
+                                       double* out_doc_stats, int32_t* out_knn_idx, float* out_knn_val, void* stream) {
   if (!S || !offsets || !s_offsets || !out_sharp || !out_centrality || !out_doc_stats || !out_knn_idx || !out_knn_val)
     return fail(SS_ERR_INVALID_ARG, "ss_group_threshold_pass: null pointer");
   if (n_docs <= 0 || !(tau > 0.f)) return fail(SS_ERR_INVALID_ARG, "ss_group_threshold_pass: n_docs and tau must be positive");
@@ -822,6 +894,7 @@ extern "C" int ss_group_threshold_pass(const float* S, const int32_t* offsets, c
   p.n_docs = n_docs;
   p.tau = tau;
   p.knn_mode = knn_mode;
+  p.symmetric = s_is_symmetric != 0;
   p.sharp = out_sharp;
   p.centrality = out_centrality;
   p.doc_stats = out_doc_stats;

@@ -122,10 +122,13 @@ def segmented_simmatrix(E: torch.Tensor, plan: RaggedPlan, out: Optional[torch.T
     return out
 
 
-def group_threshold_pass(S: torch.Tensor, plan: RaggedPlan, tau: float = 0.15, knn_mode: int = 0) -> Dict[str, torch.Tensor]:
+def group_threshold_pass(S: torch.Tensor, plan: RaggedPlan, tau: float = 0.15, knn_mode: int = 0,
+                         symmetric: bool = False) -> Dict[str, torch.Tensor]:
     """Grouping threshold pass for every document (Method/Semantic_Grouping_Optimized.py:100-115,
     270-283,343-360).  Returns device tensors: sim_sharp (packed), centrality [rows] f64,
-    doc_stats [D,8] f64 = (mu, sigma, q80, q65, q60, 0.1*std, count, k), knn_idx/knn_val [rows,33]."""
+    doc_stats [D,8] f64 = (mu, sigma, q80, q65, q60, 0.1*std, count, k), knn_idx/knn_val [rows,33].
+    ``symmetric=True`` promises ``S == S.T`` bit for bit (the output of ``segmented_simmatrix``): quantiles and moments of
+    the positive values are then computed from the strict upper triangle (half the histogram and gather work)."""
     dev = _require_cuda(S)
     if S.dtype != torch.float32 or not S.is_contiguous() or S.numel() < plan.total_s:
         raise ValueError("S must be the packed float32 output of segmented_simmatrix")
@@ -137,7 +140,7 @@ def group_threshold_pass(S: torch.Tensor, plan: RaggedPlan, tau: float = 0.15, k
         kidx = torch.empty((plan.total_rows, KNN_WIDTH), dtype=torch.int32, device=dev)
         kval = torch.empty((plan.total_rows, KNN_WIDTH), dtype=torch.float32, device=dev)
         st = lib.ss_group_threshold_pass(S.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), plan.n_docs,
-                                         float(tau), int(knn_mode), sharp.data_ptr(), cent.data_ptr(), stats.data_ptr(),
+                                         float(tau), int(knn_mode), int(bool(symmetric)), sharp.data_ptr(), cent.data_ptr(), stats.data_ptr(),
                                          kidx.data_ptr(), kval.data_ptr(), _stream_ptr(dev))
         _lib.check(st, "ss_group_threshold_pass")
     return {"sim_sharp": sharp, "centrality": cent, "doc_stats": stats, "knn_idx": kidx, "knn_val": kval}
@@ -433,7 +436,7 @@ def grouping_pass_host(E_host: torch.Tensor, sizes: Sequence[int], tau: float = 
     plan = plan or make_plan(sizes, dev)
     E = E_host.to(dev, non_blocking=True)
     S = segmented_simmatrix(E, plan)
-    res = group_threshold_pass(S, plan, tau=tau, knn_mode=knn_mode)
+    res = group_threshold_pass(S, plan, tau=tau, knn_mode=knn_mode, symmetric=True)   # K3 mirrors its tiles
     res["S"] = S
     host = _to_host(res, out)
     torch.cuda.current_stream(dev).synchronize()

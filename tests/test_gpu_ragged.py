@@ -104,15 +104,17 @@ def test_group_pass_golden_fixture(golden_dir):
         np.testing.assert_allclose(W[both], W_ref[both], atol=TOL, rtol=0)
 
 
-def test_group_pass_selection_logic_is_exact():
-    """Quantiles and neighbour lists must equal numpy's on the kernel's own sim_sharp, bit for bit."""
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_group_pass_selection_logic_is_exact(symmetric):
+    """Quantiles and neighbour lists must equal numpy's on the kernel's own sim_sharp, bit for bit — with and without the
+    promise that S is symmetric (K3's output is: the kernel then counts the strict upper triangle only)."""
     from semanticsearch_b200 import ragged
     rng = np.random.default_rng(17)
-    sizes = [16, 17, 33, 100, 257, 512, 2, 3, 64, 300, 513, 700]  # > 512 rows: the generic (memory-resident) row path
+    sizes = [16, 17, 33, 100, 257, 512, 2, 3, 64, 300, 513, 700, 129, 384, 385, 40]  # > 512 rows: the generic (memory-resident) row path
     rows = topic_docs(rng, sizes, 96)
     rows[3][7] = 0.0
     plan, _, S, blocks = run_sim(rows)
-    out = ragged.group_threshold_pass(S, plan)
+    out = ragged.group_threshold_pass(S, plan, symmetric=symmetric)
     torch.cuda.synchronize()
     sharp_all = out["sim_sharp"].cpu().numpy()
     stats = out["doc_stats"].cpu().numpy()
@@ -269,3 +271,55 @@ def test_splitter_passes_accept_output_buffers():
         ragged.adjacent_cosine(E, out=torch.empty(3, device="cuda"))
     with pytest.raises(ValueError):
         ragged.segmented_percentile(adj1, plan, 95.0, out=(bufs[0][:1], bufs[1], bufs[2], bufs[3]))
+
+
+def test_group_pass_symmetric_promise_changes_nothing():
+    """With a bit-symmetric S (K3's output) the upper-triangle form must return the same bits as the full form: sim_sharp,
+    centrality, neighbour lists, mu / sigma / quantiles / count; 0.1 * std only differs by float64 summation order."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(23)
+    sizes = [int(x) for x in rng.integers(2, 513, size=60)] + [33, 128, 129, 256, 257, 384, 385, 512]
+    rows = topic_docs(rng, sizes, 64)
+    plan, _, S, _ = run_sim(rows)
+    a = ragged.group_threshold_pass(S, plan, symmetric=False)
+    b = ragged.group_threshold_pass(S, plan, symmetric=True)
+    torch.cuda.synchronize()
+    for key in ("sim_sharp", "centrality", "knn_idx", "knn_val"):
+        assert torch.equal(a[key], b[key]), key
+    sa, sb = a["doc_stats"].cpu().numpy(), b["doc_stats"].cpu().numpy()
+    for col in (0, 1, 2, 3, 4, 6, 7):
+        assert np.array_equal(sa[:, col], sb[:, col]), col
+    np.testing.assert_allclose(sa[:, 5], sb[:, 5], rtol=1e-12, atol=1e-15)
+
+
+def test_group_pass_heavy_ties_with_symmetric_promise():
+    """Thousands of identical similarities (the radix-select fallback) and two heavy clusters of duplicates, upper-triangle form."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(29)
+    S0 = np.full((100, 100), 0.3, dtype=np.float32)
+    np.fill_diagonal(S0, 1.0)
+    S1 = np.where(rng.random((80, 80)) < 0.5, 0.2, 0.7).astype(np.float32)
+    S1 = np.maximum(S1, S1.T)
+    np.fill_diagonal(S1, 1.0)
+    S2 = np.where(rng.random((400, 400)) < 0.3, 0.1, 0.9).astype(np.float32)
+    S2 = np.maximum(S2, S2.T)
+    np.fill_diagonal(S2, 1.0)
+    mats = [S0, S1, S2]
+    sizes = [m.shape[0] for m in mats]
+    plan = ragged.make_plan(sizes, "cuda")
+    S = torch.from_numpy(np.concatenate([m.reshape(-1) for m in mats])).cuda()
+    out = ragged.group_threshold_pass(S, plan, symmetric=True)
+    torch.cuda.synchronize()
+    sharp_all = out["sim_sharp"].cpu().numpy()
+    stats = out["doc_stats"].cpu().numpy()
+    kidx, kval = out["knn_idx"].cpu().numpy(), out["knn_val"].cpu().numpy()
+    for d, n in enumerate(sizes):
+        sharp = sharp_all[plan.s_offsets[d]:plan.s_offsets[d + 1]].reshape(n, n)
+        thr = go.thresholds_ref(sharp)
+        assert stats[d, 6] == thr["count"]
+        assert stats[d, 2] == thr["edge_floor"] and stats[d, 3] == thr["tau_merge"] and stats[d, 4] == thr["global_merge_thr"]
+        idx_ref, val_ref = go.knn_lists_ref(sharp, go.k_eff_auto(n))
+        w = idx_ref.shape[1]
+        rows_d = slice(plan.offsets[d], plan.offsets[d + 1])
+        np.testing.assert_array_equal(kidx[rows_d, :w], idx_ref)
+        np.testing.assert_array_equal(kval[rows_d, :w], val_ref)
