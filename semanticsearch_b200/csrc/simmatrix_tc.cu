@@ -86,6 +86,8 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 __device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   if (elect_one()) {
     asm volatile(
@@ -235,12 +237,14 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
           for (int j = 0; j < 8; ++j) {
             const int c = (j ^ (r & 7)) * 16;  // conflict-free: 8 consecutive rows touch 8 distinct 16-byte chunks
             const float4 v = *reinterpret_cast<const float4*>(base + c);
-            float4 hi, lo;
-            hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-            lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+            // The tensor core reads a kind::tf32 operand through its upper 19 bits (sign, exponent, 10 mantissa bits): the raw
+            // plane IS the `hi` operand, hi = x with the low 13 bits dropped, and needs no rewrite.  lo = x - hi is exact in
+            // fp32 and is rounded to tf32 here (round-to-nearest, so the hardware's truncation of `lo` drops nothing).
+            float4 lo;
+            lo.x = tf32_rna(v.x - tf32_trunc(v.x)); lo.y = tf32_rna(v.y - tf32_trunc(v.y));
+            lo.z = tf32_rna(v.z - tf32_trunc(v.z)); lo.w = tf32_rna(v.w - tf32_trunc(v.w));
             ssq0 = fmaf(v.x, v.x, fmaf(v.y, v.y, ssq0));
             ssq1 = fmaf(v.z, v.z, fmaf(v.w, v.w, ssq1));
-            *reinterpret_cast<float4*>(base + c) = hi;
             *reinterpret_cast<float4*>(base + 2 * S_PLANE + c) = lo;
           }
           fence_proxy_async();  // generic-proxy writes above -> visible to the tensor core's async-proxy reads
