@@ -293,7 +293,11 @@ def verify_search(corpus, q_dev, k, shard, lo, world, dev, n_check=8, tol=2e-3, 
     except where the exact scores of the swapped rows tie within `tie_tol`."""
     import torch
     import torch.distributed as dist
-    s, i = corpus.search(q_dev, k)
+    s, i = corpus.search(q_dev, k, exchange="nccl")
+    if world > 1 and corpus.peer_exchange is not None and q_dev.shape[0] <= corpus.peer_exchange.max_queries:
+        s2, i2 = corpus.search(q_dev, k, exchange="peer")   # both exchange paths must return the same bits
+        if not (torch.equal(i, i2) and torch.equal(s, s2)):
+            raise RuntimeError("peer exchange and NCCL exchange disagree")
     torch.cuda.synchronize()
     mult = torch.arange(1, i.numel() + 1, device=dev, dtype=torch.int64).view_as(i)
     h = ((i * mult) % 2147483647).sum().view(1)
@@ -361,10 +365,11 @@ def run_ours(args):
     tdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     shard = make_shard(hi - lo, args.dim, 6 + rank, dev, tdtype)
     peer = None
-    if world > 1 and args.exchange == "peer":
+    if world > 1:   # the eager leg uses it with --exchange peer; the graphed end-to-end leg always does
         from semanticsearch_b200.sharded import PeerExchange
         peer = PeerExchange(dev, max(args.batch, 1), args.k)
     corpus = ShardedCorpus(shard, lo, peer_exchange=peer)
+    eager_exchange = args.exchange if world > 1 else "auto"
     q_host = q_dev = out_s_host = out_i_host = None
     cur_algo = [args.algo]
     lib = _lib.load()
@@ -377,7 +382,7 @@ def run_ours(args):
     graphed = [None]
 
     def step_eager():
-        return corpus.search(q_dev, args.k, algo=cur_algo[0])
+        return corpus.search(q_dev, args.k, algo=cur_algo[0], exchange=eager_exchange)
 
     def step_resident():
         return step_eager()
@@ -387,7 +392,7 @@ def run_ours(args):
             s, i = graphed[0](q_host)  # H2D copy into the static input, then one graph launch
         else:
             q = q_host.to(dev, non_blocking=True)
-            s, i = corpus.search(q, args.k, algo=cur_algo[0])
+            s, i = corpus.search(q, args.k, algo=cur_algo[0], exchange=eager_exchange)
         out_s_host.copy_(s, non_blocking=True)
         out_i_host.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the result every step
@@ -433,7 +438,7 @@ def run_ours(args):
         total_ms, kern_ms = timed(step_resident, steps, profile=True)
         clocks = sampler.stop() if sampler else None
         # end-to-end leg: the public GraphedSearch call (H2D copy into its static input + one graph launch + D2H)
-        if args.graphs == "on" and world == 1:  # capturing the NCCL all-gather hung at 2 ranks: multi-GPU runs stay eager
+        if args.graphs == "on" and (world == 1 or batch <= peer.max_queries):  # several GPUs: the kernel-only peer exchange is captured
             from semanticsearch_b200.sharded import GraphedSearch
             try:
                 graphed[0] = GraphedSearch(corpus, batch, args.k, algo=cur_algo[0])
@@ -488,7 +493,8 @@ def run_ours(args):
         return {"value": qps, "ms_per_step": total_ms / steps,
                 "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": batch * args.dim * 2,
                         "d2h_bytes_per_step": batch * args.k * 12, "ms_per_step": e2e_ms / steps,
-                        "api": "sharded.GraphedSearch (one CUDA-graph launch per search)" if graphed[0] is not None else "sharded.ShardedCorpus.search"},
+                        "api": ("sharded.GraphedSearch (one CUDA-graph launch per search" + (", NVLink peer exchange fused with the merge)" if world > 1 else ")"))
+                        if graphed[0] is not None else "sharded.ShardedCorpus.search"},
                 "gpu_launches": steps * launches_per_step, "roofline": roof}
 
     # The single-query (HBM-bound) line is measured first: measured after the power-capped GEMM phase it reads

@@ -157,7 +157,7 @@ int ss_topk_merge(const uint64_t* keys_in, int n_lists, int n_queries, int k_in,
  * kernel (one CTA per query) waits on its own buffer's flags and merges the `world` lists.
  * peer_bases_device: DEVICE array of `world` pointers (entry r = rank r's buffer as mapped in this
  * process, entry `rank` = the local allocation).  seq: 1, 2, 3, ... identical on every rank for the same
- * search.  All ranks must call in lock-step (the wait is bounded and traps after seconds). */
+ * search.  All ranks must call in lock-step (the wait is bounded; see ss_peer_status). */
 size_t ss_peer_buffer_bytes(int world, int max_queries, int k);
 int ss_peer_alloc(size_t bytes, void** dev_ptr_out, unsigned char* handle_out64);
 int ss_peer_open(const unsigned char* handle64, void** dev_ptr_out);
@@ -166,6 +166,15 @@ int ss_peer_free(void* dev_ptr);
 int ss_topk_peer_exchange_merge(const uint64_t* local_keys, int n_queries, int k, int rank, int world,
                                 void* const* peer_bases_device, int max_queries, uint32_t seq,
                                 uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
+/* The same exchange with the sequence number kept on the device (in `local_buffer`, this rank's own allocation): the
+ * launch parameters never change from one search to the next, so the two kernels can be captured in a CUDA graph
+ * together with the local search and replayed (every rank replays in lock-step).  A merge that gives up waiting for a
+ * peer (after many seconds) does not trap: it records 1 + the missing rank in the buffer's status word, which
+ * ss_peer_status copies to the host (0 = healthy; synchronises). */
+int ss_topk_peer_exchange_merge_auto(const uint64_t* local_keys, int n_queries, int k, int rank, int world,
+                                     void* const* peer_bases_device, int max_queries, void* local_buffer,
+                                     uint64_t* out_keys, float* out_scores, int64_t* out_indices, void* stream);
+int ss_peer_status(const void* local_buffer, int* status_out_host);
 
 /* Row inverse L2 norms, 1/sqrt(sum x^2) with zero rows -> zero_value (1.0 reproduces sklearn,
  * Tool/rank_chunks_optimized.py:216; 1e9 reproduces norms[norms==0]=1e-9 at

@@ -53,6 +53,9 @@ _SIGNATURES = {
     "ss_peer_free": (c_int, [c_void_p]),
     "ss_topk_peer_exchange_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_uint32, c_void_p, c_void_p,
                                             c_void_p, c_void_p]),
+    "ss_topk_peer_exchange_merge_auto": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p]),
+    "ss_peer_status": (c_int, [c_void_p, c_void_p]),
     "ss_segmented_plan_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int)]),
     "ss_segmented_simmatrix": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "ss_segmented_plan128_host": (c_int, [c_void_p, c_int, c_void_p, c_int64, POINTER(c_int64)]),

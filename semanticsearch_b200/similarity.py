@@ -13,7 +13,7 @@ from . import _lib
 
 _DTYPES = {torch.float32: _lib.SS_F32, torch.bfloat16: _lib.SS_BF16, torch.float16: _lib.SS_F16}
 
-_workspaces: Dict[Tuple[int, str], torch.Tensor] = {}
+_workspaces: Dict[Tuple[int, int, str], torch.Tensor] = {}
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -40,8 +40,12 @@ def _stream_ptr(dev: torch.device) -> int:
 
 
 def workspace(dev: torch.device, nbytes: int, tag: str = "default") -> torch.Tensor:
-    """Grow-only per-device scratch buffer (caller-provided workspace of the C ABI)."""
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), tag)
+    """Grow-only scratch buffer (the caller-provided workspace of the C ABI), one per (device, STREAM, tag): kernels of
+    different streams never share ticket counters or partial lists, and a buffer is only ever replaced by a call on the
+    stream that uses it (stream order protects the old contents).  Searches that must keep a buffer alive across calls
+    (a CUDA graph, a resident index) own theirs through a ``ResidentIndex`` instead."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, int(torch.cuda.current_stream(dev).cuda_stream), tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
@@ -91,22 +95,34 @@ def choose_algo(corpus: torch.Tensor, queries: torch.Tensor, k: int) -> str:
 
 
 class ResidentIndex:
-    """Token of a corpus that stays resident and unchanged in HBM (``sharded.ShardedCorpus`` owns one).  It carries its
-    own K2 workspace, whose head keeps the corpus's inverse row norms: while buffer and corpus (pointer, shape, dtype) are
-    those of the token's previous K2 call, the next call skips the norm pre-pass (one read of the whole corpus).  No
-    other caller touches this workspace, so a CUDA graph captured from such a call stays valid."""
+    """Token of a corpus that stays resident and unchanged in HBM (``sharded.ShardedCorpus`` owns one, and so does every
+    ``sharded.GraphedSearch``).  It carries its own workspaces — nobody else touches them, so a CUDA graph captured from a
+    search with this token stays valid whatever other searches the process runs — and the K2 workspace keeps the corpus's
+    inverse row norms at its head: while buffer and corpus (pointer, shape, dtype) are those of the token's previous K2
+    call, the next call skips the norm pre-pass (one read of the whole corpus)."""
 
-    __slots__ = ("ws", "state")
+    __slots__ = ("bufs", "state", "frozen")
 
     def __init__(self):
-        self.ws = None      # grow-only uint8 workspace of this corpus's K2 calls
-        self.state = None   # (workspace data_ptr, corpus data_ptr, rows, dim, dtype) of the last K2 call
+        self.bufs: Dict[str, torch.Tensor] = {}   # grow-only uint8 workspaces by tag
+        self.state = None    # (workspace data_ptr, corpus data_ptr, rows, dim, dtype) of the last K2 call
+        self.frozen = False  # set once a CUDA graph has baked the buffer addresses in
 
-    def workspace(self, dev: torch.device, nbytes: int) -> torch.Tensor:
-        if self.ws is None or self.ws.numel() < nbytes or self.ws.device != dev:
-            self.ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
-            self.state = None
-        return self.ws
+    @property
+    def ws(self):
+        return self.bufs.get("gemm")
+
+    def workspace(self, dev: torch.device, nbytes: int, tag: str = "gemm") -> torch.Tensor:
+        buf = self.bufs.get(tag)
+        if buf is None or buf.numel() < nbytes or buf.device != dev:
+            if self.frozen:
+                raise RuntimeError("this index's workspaces are referenced by a captured CUDA graph and cannot grow; "
+                                   "search with the batch size and k the graph was built for")
+            buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+            self.bufs[tag] = buf
+            if tag == "gemm":
+                self.state = None
+        return buf
 
     def invalidate(self) -> None:
         """Call after the corpus bytes change."""
@@ -149,7 +165,7 @@ def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_ba
         keys_ptr = keys.data_ptr() if keys is not None else None
         if algo == "gemm":
             need = lib.ss_cosine_topk_gemm_workspace_bytes(n, d, b, k)
-            ws = resident.workspace(dev, need) if resident is not None else workspace(dev, need, "gemm")
+            ws = resident.workspace(dev, need, "gemm") if resident is not None else workspace(dev, need, "gemm")
             state = (ws.data_ptr(), corpus.data_ptr(), n, d, corpus.dtype)
             valid = resident is not None and resident.state == state
             st = lib.ss_cosine_topk_gemm_resident(
@@ -164,7 +180,7 @@ def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_ba
             for q0 in range(0, b, step):
                 q1 = min(b, q0 + step)
                 need = lib.ss_cosine_topk_tcstream_workspace_bytes(n, d, q1 - q0, k)
-                ws = workspace(dev, need)
+                ws = resident.workspace(dev, need, "tcstream") if resident is not None else workspace(dev, need)
                 st = lib.ss_cosine_topk_tcstream(
                     corpus.data_ptr(), n, d, _dtype_code(corpus), queries[q0:q1].data_ptr(), q1 - q0, k, int(index_base),
                     ws.data_ptr(), ws.numel(), keys[q0:q1].data_ptr() if keys is not None else None,
@@ -172,14 +188,14 @@ def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_ba
                 _lib.check(st, "ss_cosine_topk_tcstream")
         elif algo == "small":
             need = lib.ss_cosine_topk_small_workspace_bytes(n, b)
-            ws = workspace(dev, need)
+            ws = resident.workspace(dev, need, "small") if resident is not None else workspace(dev, need)
             st = lib.ss_cosine_topk_small(
                 corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, _dtype_code(queries), k,
                 int(index_base), ws.data_ptr(), ws.numel(), keys_ptr, scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))
             _lib.check(st, "ss_cosine_topk_small")
         else:
             need = lib.ss_cosine_topk_stream_workspace_bytes(n, d, _dtype_code(corpus), b, k)
-            ws = workspace(dev, need)
+            ws = resident.workspace(dev, need, "stream") if resident is not None else workspace(dev, need)
             st = lib.ss_cosine_topk_stream(
                 corpus.data_ptr(), n, d, _dtype_code(corpus), queries.data_ptr(), b, _dtype_code(queries), k,
                 int(index_base), ws.data_ptr(), ws.numel(), keys_ptr, scores.data_ptr(), idx.data_ptr(), _stream_ptr(dev))

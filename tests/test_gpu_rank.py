@@ -186,3 +186,45 @@ def test_resident_corpus_keeps_its_norms_between_gemm_searches():
     s, i = ca.search(Q, 10, algo="gemm")
     w = similarity.cosine_topk(A, Q, 10, algo="gemm")
     assert torch.equal(i, w[1]) and torch.equal(s, w[0])
+
+
+def test_graph_survives_larger_eager_searches_and_streams_do_not_share_scratch():
+    """(1) A captured search keeps working after eager searches that need bigger workspaces (the graph owns its buffers);
+    (2) two streams running different searches at the same time return what each returns alone (scratch is per stream)."""
+    from semanticsearch_b200 import sharded, similarity
+    g = torch.Generator(device="cuda").manual_seed(9)
+    C = torch.randn((300000, 128), generator=g, device="cuda").to(torch.bfloat16)
+    for batch, k in ((1, 10), (16, 100), (256, 10)):
+        Q = torch.randn((batch, 128), generator=g, device="cuda").to(torch.bfloat16)
+        corpus = sharded.ShardedCorpus(C, 0)
+        gs = sharded.GraphedSearch(corpus, batch, k)
+        s0, i0 = gs(Q)
+        s0, i0 = s0.clone(), i0.clone()
+        big = torch.randn((4 * batch + 700, 128), generator=g, device="cuda").to(torch.bfloat16)
+        for algo in ("stream", "tcstream", "gemm"):      # eager calls on the same corpus and on the module-level scratch
+            if algo == "gemm" and k > 16:
+                continue
+            similarity.cosine_topk(C, big, k, algo=algo)
+        with pytest.raises(RuntimeError, match="captured CUDA graph"):
+            corpus.search(big, k, resident=gs._resident)  # the graph's own buffers refuse to grow
+        s1, i1 = gs(Q)
+        torch.cuda.synchronize()
+        assert torch.equal(i0, i1) and torch.equal(s0, s1)
+    # two streams
+    Qa = torch.randn((8, 128), generator=g, device="cuda").to(torch.bfloat16)
+    Qb = torch.randn((24, 128), generator=g, device="cuda").to(torch.bfloat16)
+    want_a = similarity.cosine_topk(C, Qa, 10)
+    want_b = similarity.cosine_topk(C, Qb, 50)
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(10):
+        with torch.cuda.stream(sa):
+            ra = similarity.cosine_topk(C, Qa, 10)
+        with torch.cuda.stream(sb):
+            rb = similarity.cosine_topk(C, Qb, 50)
+        outs.append((ra, rb))
+    torch.cuda.synchronize()
+    for ra, rb in outs:
+        assert torch.equal(ra[1], want_a[1]) and torch.equal(ra[0], want_a[0])
+        assert torch.equal(rb[1], want_b[1]) and torch.equal(rb[0], want_b[0])
