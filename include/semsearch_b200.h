@@ -248,6 +248,15 @@ int ss_group_coassociation(const int32_t* labels, int n_labelings, int n, double
 int ss_similarity_distribution(const float* S, const int32_t* offsets, const int64_t* s_offsets, int n_docs, float eps,
                                double* out_stats, void* stream);
 
+/* a12 — diameter-bounded splitting of each document's sentences, the controller's optional stage on sim = emb @ emb.T
+ * (data_process/simple_chunk_controller.py:571-594,614): a span [a, b) whose diameter 1 - min_{i != j} S[i][j] exceeds
+ * `threshold` is cut after its lowest adjacent similarity S[i][i+1] (first minimum) and both halves are treated the
+ * same way.  out_span_ends[offsets[d] + s] = end (exclusive, document-local) of the s-th final span of document d,
+ * ascending; out_n_spans[d] = their number (1 = not split); out_diameter[d] = diameter of the whole document
+ * (0 for a single row).  S has the layout of K3; max_doc_rows <= 4096. */
+int ss_diameter_split(const float* S, const int32_t* offsets, const int64_t* s_offsets, int n_docs, int max_doc_rows,
+                      double threshold, int32_t* out_span_ends, int32_t* out_n_spans, double* out_diameter, void* stream);
+
 /* C99 rank transform of each document's S (layout of K3): global row+column rank
  * (Method/Semantic_Splitter_Optimized.py:189-192) or the clipped mask_size x mask_size local rank
  * (:171-186) when bit 0 of use_local_rank is set.  Bit 1 (value 2, global mode only) promises that every S equals its

@@ -66,3 +66,25 @@ def analyze_similarity_distribution_ref(S) -> Optional[Dict[str, float]]:
     for p in PCTS:
         out[f"p{p}"] = float(np.percentile(kept, p))
     return out
+
+
+def split_indices_by_diameter_ref(sim_matrix: np.ndarray, start: int, end: int, threshold: float):
+    """Restatement of the controller's ``_split_indices_by_diameter`` (data_process/simple_chunk_controller.py:571-594):
+    a span whose diameter ``1 - min off-diagonal similarity`` exceeds ``threshold`` is cut after the first minimum of its
+    adjacent similarities and both halves are split recursively, left first."""
+    length = end - start
+    if length <= 1:
+        return [(start, end)]
+    sub = sim_matrix[start:end, start:end]
+    if length == 2:
+        diam = 1.0 - float(sub[0, 1])
+    else:
+        mask = ~np.eye(length, dtype=bool)
+        diam = 1.0 - float(sub[mask].min())
+    if diam <= threshold:
+        return [(start, end)]
+    adj = [float(sim_matrix[i, i + 1]) for i in range(start, end - 1)]
+    if not adj:
+        return [(start, end)]
+    cut = start + int(np.argmin(np.array(adj))) + 1
+    return split_indices_by_diameter_ref(sim_matrix, start, cut, threshold) + split_indices_by_diameter_ref(sim_matrix, cut, end, threshold)

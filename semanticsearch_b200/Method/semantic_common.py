@@ -13,7 +13,7 @@ The OpenIE string helpers of the reference module are outside the hot path and n
 from __future__ import annotations
 
 import logging
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -128,6 +128,29 @@ def create_similarity_matrix(sentences: List[str], model_name: str, batch_size: 
     return similarity_matrices_from_embeddings([np.asarray(embs, dtype=np.float32)])[0]
 
 
+def split_indices_by_diameter(doc_embeddings: Sequence[np.ndarray], threshold: float) -> List[List[Tuple[int, int]]]:
+    """Batched device form of the controller's ``_split_indices_by_diameter`` / ``_enforce_diameter_on_tuples``
+    (data_process/simple_chunk_controller.py:571-625): for every document (``n x dim`` embeddings, un-normalised) the
+    list of ``(start, end)`` sentence spans whose diameter ``1 - min off-diagonal cosine`` does not exceed ``threshold``,
+    obtained by cutting at the lowest adjacent similarity.  Documents with fewer than two sentences keep one span."""
+    import torch
+    from .. import ragged
+    sizes = [int(e.shape[0]) if e is not None and getattr(e, "ndim", 0) == 2 else 0 for e in doc_embeddings]
+    out: List[List[Tuple[int, int]]] = [[(0, n)] if n > 0 else [] for n in sizes]
+    live = [d for d, n in enumerate(sizes) if n >= 2]
+    if not live:
+        return out
+    rows = [np.ascontiguousarray(doc_embeddings[d], dtype=np.float32) for d in live]
+    plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
+    S = ragged.segmented_simmatrix(torch.from_numpy(np.concatenate(rows, axis=0)).cuda(), plan)
+    ends, n_spans, _ = ragged.diameter_split(S, plan, float(threshold))
+    ends_h, n_h = ends.cpu().numpy(), n_spans.cpu().numpy()
+    for slot, d in enumerate(live):
+        e = [int(x) for x in ends_h[plan.offsets[slot]: plan.offsets[slot] + int(n_h[slot])]]
+        out[d] = list(zip([0] + e[:-1], e))
+    return out
+
+
 def analyze_similarity_distribution(sim_matrix) -> Optional[Dict[str, float]]:
     """Reference :250-270, computed on the device (strict upper triangle, values >= 1-1e-5 dropped,
     min/max/mean/std + percentiles 10/25/50/75/80/85/90/95)."""
@@ -146,7 +169,7 @@ def analyze_similarity_distribution(sim_matrix) -> Optional[Dict[str, float]]:
 
 __all__ = [
     "normalize_device", "estimate_optimal_batch_size", "optimize_gpu_batch_size", "embed_sentences_batched",
-    "create_similarity_matrix", "similarity_matrices_from_embeddings", "analyze_similarity_distribution",
+    "create_similarity_matrix", "similarity_matrices_from_embeddings", "analyze_similarity_distribution", "split_indices_by_diameter",
     "init_logger", "log_msg",
 ]
 

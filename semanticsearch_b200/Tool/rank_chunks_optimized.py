@@ -29,6 +29,7 @@ import numpy as np
 import pandas as pd
 
 from . import Sentence_Embedding as _embedding
+from .._lib import DeviceError as _DeviceError
 
 try:
     csv.field_size_limit(2147483647)
@@ -125,25 +126,110 @@ def _standardize_columns(df: pd.DataFrame, *, require_query_text: bool = True) -
     return df.rename(columns=mapping)
 
 
+def _f64_rank_surrogate(scores: np.ndarray) -> np.ndarray:
+    """float32 values whose descending order (ties: lower row first) is exactly that of the float64 ``scores``.  The device
+    rank kernels take fp32 keys; BM25 scores are float64 in the reference (:219-235) and can differ below fp32 resolution,
+    so they are ranked here in float64 (stable) and handed over as ``-rank`` — exact in fp32 for up to 2^24 rows."""
+    order = np.argsort(-np.asarray(scores, dtype=np.float64), kind="stable")
+    rank = np.empty(len(order), dtype=np.int64)
+    rank[order] = np.arange(len(order))
+    return (-rank).astype(np.float32)
+
+
+class DeviceRowStore:
+    """HBM row store behind ``OptimizedRanker.chunk_embedding_cache`` (reference :116-139): one fp32 device matrix holds the
+    embedding of every cached chunk, ``md5(text) -> slot`` lives on the host.  A chunk crosses the host link at most once —
+    and not at all when the encoder returns CUDA tensors; ranking a query against cached chunks is a device-side row
+    gather.  Eviction follows the reference: once more than ``cache_size`` chunks are cached, the oldest quarter goes."""
+
+    def __init__(self, cache_size: int):
+        self.cache_size = int(cache_size)
+        self.slots: Dict[str, int] = {}      # insertion-ordered, like the reference's dict
+        self.free: List[int] = []
+        self.rows = None                     # torch float32 [capacity, dim] on the device
+        self.h2d_rows = 0                    # chunk rows uploaded from host memory so far
+        self.d2d_rows = 0                    # chunk rows taken over from CUDA tensors of the encoder
+
+    def __len__(self) -> int:
+        return len(self.slots)
+
+    def __contains__(self, key: str) -> bool:
+        return key in self.slots
+
+    def keys(self):
+        return self.slots.keys()
+
+    def __getitem__(self, key: str) -> np.ndarray:
+        return self.rows[self.slots[key]].cpu().numpy()
+
+    def _reserve(self, n_new: int, dim: int, device):
+        import torch
+        need = len(self.slots) + n_new
+        if self.rows is None:
+            self.rows = torch.empty((max(1024, 2 * need), dim), dtype=torch.float32, device=device)
+            self.free = list(range(self.rows.shape[0] - 1, -1, -1))
+        elif self.rows.shape[1] != dim:
+            raise RuntimeError(f"embedding width changed from {self.rows.shape[1]} to {dim}")
+        if len(self.free) < n_new:
+            old = self.rows
+            grown = torch.empty((max(2 * old.shape[0], need + 1024), dim), dtype=torch.float32, device=old.device)
+            grown[: old.shape[0]] = old
+            self.free = list(range(grown.shape[0] - 1, old.shape[0] - 1, -1)) + self.free
+            self.rows = grown
+
+    def add(self, keys: List[str], vectors) -> None:
+        """Cache ``vectors[i]`` under ``keys[i]`` (keys not yet cached; duplicates inside the call keep the last row)."""
+        import torch
+        if not keys:
+            return
+        on_device = isinstance(vectors, torch.Tensor) and vectors.is_cuda
+        vec = vectors.to(torch.float32) if on_device else torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32))
+        device = vec.device if on_device else torch.device("cuda", torch.cuda.current_device())
+        self._reserve(len(keys), vec.shape[1], device)
+        slots = []
+        for key in keys:
+            slot = self.slots.get(key)
+            if slot is None:
+                slot = self.free.pop()
+                self.slots[key] = slot
+            slots.append(slot)
+        idx = torch.tensor(slots, dtype=torch.int64, device=self.rows.device)
+        self.rows.index_copy_(0, idx, vec.to(self.rows.device, non_blocking=True))
+        if on_device:
+            self.d2d_rows += len(keys)
+        else:
+            self.h2d_rows += len(keys)
+
+    def gather(self, keys: List[str]):
+        """Device matrix ``[len(keys), dim]`` of the cached rows, in the order of ``keys``."""
+        import torch
+        idx = torch.tensor([self.slots[k] for k in keys], dtype=torch.int64, device=self.rows.device)
+        return self.rows.index_select(0, idx)
+
+    def evict_if_needed(self) -> None:
+        """Reference :131-139: beyond ``cache_size`` entries, drop the oldest 25 %."""
+        if len(self.slots) > self.cache_size:
+            for key in list(self.slots.keys())[: len(self.slots) // 4]:
+                self.free.append(self.slots.pop(key))
+
+
 class OptimizedRanker:
-    """Per-query hybrid ranker with md5-keyed embedding caches (reference :107-250)."""
+    """Per-query hybrid ranker with md5-keyed embedding caches (reference :107-250).  The chunk cache is a
+    ``DeviceRowStore``: chunk embeddings stay resident in HBM between queries."""
 
     def __init__(self, model_name: str = "all-MiniLM-L6-v2", device_preference: str = "dml", cache_size: int = 1000):
         self.model_name = model_name
         self.device_preference = device_preference if device_preference else "dml"
         self.cache_size = cache_size
         self.query_embedding_cache: Dict[str, np.ndarray] = {}
-        self.chunk_embedding_cache: Dict[str, np.ndarray] = {}
+        self.chunk_embedding_cache = DeviceRowStore(cache_size)
         self.sentence_embedding = _embedding.sentence_embedding
 
     def _get_text_hash(self, text: str) -> str:
         return hashlib.md5(text.encode("utf-8")).hexdigest()
 
     def _manage_cache_size(self):
-        if len(self.chunk_embedding_cache) > self.cache_size:
-            for key in list(self.chunk_embedding_cache.keys())[: len(self.chunk_embedding_cache) // 4]:
-                del self.chunk_embedding_cache[key]
-            gc.collect()
+        self.chunk_embedding_cache.evict_if_needed()
 
     def get_query_embedding(self, query: str) -> np.ndarray:
         key = self._get_text_hash(query)
@@ -152,46 +238,62 @@ class OptimizedRanker:
         emb = self.sentence_embedding(text_list=[query], model_name=self.model_name, device_preference=self.device_preference)
         if emb is None or emb.shape[0] == 0:
             raise RuntimeError(f"Failed to embed query: {query}")
-        self.query_embedding_cache[key] = emb[0]
-        return emb[0]
+        vec = emb[0].detach().float().cpu().numpy() if hasattr(emb, "detach") else np.asarray(emb[0])
+        self.query_embedding_cache[key] = vec
+        return vec
+
+    def get_chunk_embeddings_device(self, chunks: List[str], batch_size: int = 32):
+        """CUDA float32 ``[len(chunks), dim]`` matrix of the chunk embeddings: cached rows are gathered on the device, only
+        chunks never seen before go through the encoder (and over the host link, unless the encoder returns CUDA tensors)."""
+        store = self.chunk_embedding_cache
+        keys = [self._get_text_hash(c) for c in chunks]
+        seen, miss_keys, miss_text = set(), [], []
+        for key, text in zip(keys, chunks):
+            if key not in store and key not in seen:
+                seen.add(key)
+                miss_keys.append(key)
+                miss_text.append(text)
+        if miss_text:
+            new = self.sentence_embedding(text_list=miss_text, model_name=self.model_name, batch_size=batch_size,
+                                          device_preference=self.device_preference)
+            if new is None or new.shape[0] != len(miss_text):
+                raise RuntimeError("Failed to embed some chunks")
+            store.add(miss_keys, new)
+        rows = store.gather(keys)
+        self._manage_cache_size()     # after the gather, like the reference (:196-199)
+        return rows
 
     def get_chunk_embeddings_batch(self, chunks: List[str], batch_size: int = 32) -> np.ndarray:
-        keys = [self._get_text_hash(c) for c in chunks]
-        missing = [(i, c) for i, (c, k) in enumerate(zip(chunks, keys)) if k not in self.chunk_embedding_cache]
-        rows: List[Optional[np.ndarray]] = [self.chunk_embedding_cache.get(k) for k in keys]
-        if missing:
-            new = self.sentence_embedding(text_list=[c for _, c in missing], model_name=self.model_name, batch_size=batch_size,
-                                          device_preference=self.device_preference)
-            if new is None or new.shape[0] != len(missing):
-                raise RuntimeError("Failed to embed some chunks")
-            for (i, _c), vec in zip(missing, new):
-                self.chunk_embedding_cache[keys[i]] = vec
-                rows[i] = vec
-        self._manage_cache_size()
-        return np.array(rows)
+        """Reference :161-199 — host ndarray ``[len(chunks), dim]`` (a device-to-host copy of the cached rows)."""
+        return self.get_chunk_embeddings_device(chunks, batch_size).cpu().numpy()
+
+    def _query_device(self, query: str):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(self.get_query_embedding(query), dtype=np.float32).reshape(1, -1)).cuda()
 
     def top_k(self, query: str, chunks: List[str], k: int = 10):
         """Fused device path for callers that only need the best k chunks: (scores, indices)."""
-        import torch
         from .. import similarity
-        q = np.asarray(self.get_query_embedding(query), dtype=np.float32).reshape(1, -1)
-        C = np.ascontiguousarray(self.get_chunk_embeddings_batch(chunks), dtype=np.float32)
-        s, i = similarity.cosine_topk(torch.from_numpy(C).cuda(), torch.from_numpy(q).cuda(), min(k, len(chunks)))
+        s, i = similarity.cosine_topk(self.get_chunk_embeddings_device(chunks).contiguous(), self._query_device(query),
+                                      min(k, len(chunks)))
         return s[0].cpu().numpy(), i[0].cpu().numpy()
 
     def rank_single_query_optimized(self, query: str, chunks_df: pd.DataFrame, text_column: str = "chunk_text",
                                     id_column: str = "chunk_id") -> pd.DataFrame:
         """Reference :201-250: adds cosine_score / bm25_score / rrf_score and sorts by rrf desc."""
+        from .. import similarity
         if text_column not in chunks_df.columns:
             raise ValueError(f"Text column '{text_column}' not found in DataFrame")
         chunks = chunks_df[text_column].fillna("").tolist()
-        query_embedding = self.get_query_embedding(query).reshape(1, -1)
-        chunk_embeddings = self.get_chunk_embeddings_batch(chunks)
-        cosine_scores = cosine_similarity(query_embedding, chunk_embeddings)[0]
+        q_dev = self._query_device(query)
+        c_dev = self.get_chunk_embeddings_device(chunks).contiguous()
+        cos_dev = similarity.cosine_scores(c_dev, q_dev)                      # ss_cosine_scores on the resident rows
+        _, cosine_rank_dev = similarity.rank_order(cos_dev)
+        cosine_scores = cos_dev[0].cpu().numpy()
+        cosine_rank = cosine_rank_dev[0].cpu().numpy().astype(np.float64)
         bm25 = BM25Okapi([c.lower().split() for c in chunks], epsilon=0.25)
         bm25_scores = np.maximum(bm25.get_scores(query.lower().split()), 0.0)
-        _, cosine_rank = _device_rank_lookup(cosine_scores)
-        _, bm25_rank = _device_rank_lookup(bm25_scores.astype(np.float32))
+        _, bm25_rank = _device_rank_lookup(_f64_rank_surrogate(bm25_scores))   # float64 order, fp32 keys
         k = 60
         out = chunks_df.copy()
         out["cosine_score"] = cosine_scores
@@ -213,23 +315,24 @@ def rank_query_groups_batched(ranker: "OptimizedRanker", groups: List[tuple], up
     from .. import similarity
     if not groups:
         return []
-    q_rows, c_rows, bm_rows, sizes = [], [], [], []
+    q_rows, c_rows, bm_rows, bm_keys, sizes = [], [], [], [], []
     for query, df in groups:
         if text_column not in df.columns:
             raise ValueError(f"Text column '{text_column}' not found in DataFrame")
         chunks = df[text_column].fillna("").tolist()
         q_rows.append(np.asarray(ranker.get_query_embedding(query), dtype=np.float32).reshape(-1))
-        c_rows.append(np.ascontiguousarray(ranker.get_chunk_embeddings_batch(chunks), dtype=np.float32))
+        c_rows.append(ranker.get_chunk_embeddings_device(chunks))           # device rows: cached chunks never cross the link again
         bm25 = BM25Okapi([c.lower().split() for c in chunks], epsilon=0.25)
         bm_rows.append(np.maximum(bm25.get_scores(query.lower().split()), 0.0))
+        bm_keys.append(_f64_rank_surrogate(bm_rows[-1]))                    # the reference ranks the float64 scores (:226-235)
         sizes.append(len(chunks))
     if max(sizes) > 8192:
         raise ValueError("a query group holds more than 8192 chunks; rank it with rank_single_query_optimized")
     offsets = np.zeros(len(sizes) + 1, dtype=np.int32)
     offsets[1:] = np.cumsum(sizes)
     out = similarity.segmented_rank_rrf(
-        torch.from_numpy(np.concatenate(c_rows, axis=0)).cuda(), torch.from_numpy(offsets).cuda(),
-        torch.from_numpy(np.stack(q_rows)).cuda(), torch.from_numpy(np.concatenate(bm_rows).astype(np.float32)).cuda(),
+        torch.cat(c_rows, dim=0).contiguous(), torch.from_numpy(offsets).cuda(),
+        torch.from_numpy(np.stack(q_rows)).cuda(), torch.from_numpy(np.concatenate(bm_keys)).cuda(),
         k_rrf=60.0, upper_percentile=float(upper_percentile), lower_percentile=float(lower_percentile), max_group_rows=max(sizes))
     cos, rrf = out["cosine"].cpu().numpy(), out["rrf"].cpu().numpy()
     order, thr = out["order"].cpu().numpy(), out["thresholds"].cpu().numpy()
@@ -263,6 +366,7 @@ def _process_queries_sequential(df: pd.DataFrame, model_name: str, upper_percent
     groups = [(qid, group) for qid, group in df.groupby("query_id") if len(group) >= 2]
     batched = [(qid, group) for qid, group in groups if len(group) <= 8192]
     single = [(qid, group) for qid, group in groups if len(group) > 8192]
+    from .._lib import DeviceError
     try:
         # every query group of the block in one device launch
         ranked_all = rank_query_groups_batched(ranker, [(str(g["query_text"].iloc[0]), g) for _qid, g in batched],
@@ -272,14 +376,21 @@ def _process_queries_sequential(df: pd.DataFrame, model_name: str, upper_percent
             if not sel.empty:
                 sel["label"] = (sel["rrf_score"] >= pos_thr).astype(int)
                 kept.append(sel)
-    except RuntimeError:
-        raise  # CUDA / embedding failures are not swallowed: there is no CPU fallback
+    except DeviceError:
+        raise  # a failing kernel or CUDA error is never swallowed: there is no CPU fallback
+    except Exception as exc:
+        # one bad group (encoder failure, missing column, ...) must not take the block down: the reference isolates every
+        # query (:488-536), so the groups are ranked one by one and only the failing ones are reported and skipped
+        print(f"Batched ranking failed ({exc}); ranking the {len(batched)} groups of this block one by one")
+        single = batched + single
     for query_id, group in single:
         try:
             ranked = ranker.rank_single_query_optimized(str(group["query_text"].iloc[0]), group)
             labelled = None if ranked.empty else _label_group(ranked, upper_percentile, lower_percentile)
             if labelled is not None:
                 kept.append(labelled)
+        except DeviceError:
+            raise
         except Exception as exc:
             print(f"Error processing query {query_id}: {exc}")
     return kept
@@ -320,6 +431,8 @@ def rank_and_filter_chunks_optimized(chunks_tsv: str, output_dir: Path, original
             if "query_text" not in block.columns and "query_id" in block.columns:
                 block["query_text"] = block["query_id"].map(query_map).fillna("")
             kept.extend(_process_queries_sequential(block, model_name, upper_percentile, lower_percentile))
+        except _DeviceError:
+            raise  # device failures propagate to the caller (the reference would fall back to the CPU; this path has none)
         except Exception as exc:
             print(f"Error processing chunk: {exc}")
     if not kept:

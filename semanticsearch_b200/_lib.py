@@ -66,6 +66,7 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "ss_group_coassociation": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ss_similarity_distribution": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "ss_diameter_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ss_c99_rank_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ss_c99_divisive_cuts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_double, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -101,7 +102,12 @@ def load():
     return _lib
 
 
+class DeviceError(RuntimeError):
+    """A C-ABI entry point failed (bad arguments, CUDA error).  Host layers that isolate per-item failures, as the reference
+    does around each query, let this one propagate: there is no CPU path to fall back to."""
+
+
 def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().ss_last_error()
-        raise RuntimeError(f"{what} failed (status {status}): {msg.decode() if msg else 'unknown error'}")
+        raise DeviceError(f"{what} failed (status {status}): {msg.decode() if msg else 'unknown error'}")

@@ -275,6 +275,26 @@ def similarity_distribution(S: torch.Tensor, plan: RaggedPlan, eps: float = 1e-5
     return out
 
 
+def diameter_split(S: torch.Tensor, plan: RaggedPlan, threshold: float):
+    """Diameter-bounded splitting of every document (data_process/simple_chunk_controller.py:571-594 on the similarity
+    matrix of :614): returns ``(span_ends int32 [rows], n_spans int32 [D], diameter float64 [D])`` device tensors —
+    document ``d`` is split into the spans that end (exclusively) at ``span_ends[offsets[d] : offsets[d] + n_spans[d]]``;
+    ``diameter[d] = 1 - min off-diagonal similarity`` of the whole document."""
+    dev = _require_cuda(S)
+    if S.dtype != torch.float32 or not S.is_contiguous() or S.numel() < plan.total_s:
+        raise ValueError("S must be the packed float32 output of segmented_simmatrix")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ends = torch.zeros(max(plan.total_rows, 1), dtype=torch.int32, device=dev)
+        n_spans = torch.empty(plan.n_docs, dtype=torch.int32, device=dev)
+        diam = torch.empty(plan.n_docs, dtype=torch.float64, device=dev)
+        st = lib.ss_diameter_split(S.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), plan.n_docs,
+                                   max(plan.max_rows, 1), float(threshold), ends.data_ptr(), n_spans.data_ptr(), diam.data_ptr(),
+                                   _stream_ptr(dev))
+        _lib.check(st, "ss_diameter_split")
+    return ends, n_spans, diam
+
+
 def c99_rank_matrix(S: torch.Tensor, plan: RaggedPlan, use_local_rank: bool = False, mask_size: int = 11,
                     symmetric: bool = False) -> torch.Tensor:
     """C99 rank transform of every document's S (Method/Semantic_Splitter_Optimized.py:171-192), packed like S.

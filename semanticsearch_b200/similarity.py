@@ -157,6 +157,15 @@ def cosine_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, index_ba
         raise ValueError("the tensor-core GEMM path needs bf16/fp16 corpus and queries of one dtype, k <= 16, dim % 8 == 0")
     if algo == "tcstream" and not _tcstream_eligible(corpus, queries, k):
         raise ValueError("the tensor-core streaming path needs bf16/fp16 corpus and queries of one dtype, k <= 1024, dim % 8 == 0")
+    if k > n:
+        # fewer rows than requested: search with k = n and pad the tail (score -inf, index -1, key 0 = the empty slot of
+        # the merge kernels), whichever kernel ran
+        res = cosine_topk(corpus, queries, n, index_base=index_base, return_keys=True, algo=algo, resident=resident)
+        pad = k - n
+        scores = torch.cat([res[0], torch.full((b, pad), float("-inf"), dtype=torch.float32, device=dev)], dim=1)
+        idx = torch.cat([res[1], torch.full((b, pad), -1, dtype=torch.int64, device=dev)], dim=1)
+        keys = torch.cat([res[2], torch.zeros((b, pad), dtype=torch.int64, device=dev)], dim=1)
+        return (scores, idx, keys) if return_keys else (scores, idx)
     lib = _lib.load()
     with torch.cuda.device(dev):
         scores = torch.empty((b, k), dtype=torch.float32, device=dev)

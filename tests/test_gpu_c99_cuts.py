@@ -83,8 +83,10 @@ def test_device_cuts_reproduce_reference_outputs(golden_dir):
         picked = [int(x) for x in cuts.cpu().numpy()[:cnt]]
         _assert_same_picks_up_to_near_ties(picked, m["cuts"], R.cpu().numpy().reshape(En.shape[0], -1), name)
         if len(g[f"{name}_D"]) and picked == m["cuts"]:
-            # the reference sums fp32 blocks, the kernel an exact float64 table
-            np.testing.assert_allclose(prof.cpu().numpy()[:cnt + 1], g[f"{name}_D"], rtol=2e-6, atol=0)
+            # the reference sums fp32 blocks, the kernel an exact float64 table; where the fixture holds no rank matrix the
+            # ranks come from the device's own S, whose last bits (and hence a few ranks) differ from BLAS's
+            pinned = f"{name}_R" in g.files
+            np.testing.assert_allclose(prof.cpu().numpy()[:cnt + 1], g[f"{name}_D"], rtol=2e-6 if pinned else 1e-5, atol=0)
 
 
 @pytest.mark.parametrize("mode,local", [("gain", False), ("profile", False), ("gain", True)])

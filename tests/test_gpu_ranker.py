@@ -183,3 +183,119 @@ def test_batched_group_ranking_equals_per_query_path():
             assert sorted(sel["chunk_id"]) == sorted(labelled["chunk_id"])
     finally:
         emb.set_embedding_backend(None)
+
+
+def _ranker_with_table(n=300, d=48, seed=5, cuda_encoder=False):
+    from semanticsearch_b200.Tool import Sentence_Embedding as emb
+    from semanticsearch_b200.Tool import rank_chunks_optimized as R
+    rng = np.random.default_rng(seed)
+    texts = [f"chunk {i:04d} " + ("alpha" if i % 2 else "beta") for i in range(n)]
+    table = {t: rng.standard_normal(d).astype(np.float32) for t in texts}
+    table["alpha query"] = rng.standard_normal(d).astype(np.float32)
+    table["beta query"] = rng.standard_normal(d).astype(np.float32)
+    calls = []
+
+    def backend(text_list, model_name, batch_size=32, device_preference=None):
+        calls.append(list(text_list))
+        if any(t == "poison" for t in text_list):
+            raise RuntimeError("encoder exploded")
+        out = np.stack([table[t] for t in text_list]).astype(np.float32)
+        return torch.from_numpy(out).cuda() if cuda_encoder else out
+
+    emb.set_embedding_backend(backend)
+    return R, R.OptimizedRanker(model_name="m", device_preference="cuda", cache_size=100000), texts, table, calls
+
+
+def test_device_row_store_serves_cached_chunks_without_host_traffic():
+    """§8f-4: a second query over cached chunks encodes nothing and uploads no chunk row; results equal the uncached path."""
+    from semanticsearch_b200.Tool import Sentence_Embedding as emb
+    R, ranker, texts, table, calls = _ranker_with_table()
+    try:
+        df = pd.DataFrame({"chunk_id": [f"c{i}" for i in range(len(texts))], "chunk_text": texts})
+        first = ranker.rank_single_query_optimized("alpha query", df)
+        store = ranker.chunk_embedding_cache
+        assert store.h2d_rows == len(texts) and len(store) == len(texts)
+        n_calls = len(calls)
+        second = ranker.rank_single_query_optimized("beta query", df.iloc[::-1].reset_index(drop=True))
+        assert store.h2d_rows == len(texts)                       # no chunk row crossed the link again
+        assert [c for c in calls[n_calls:]] == [["beta query"]]   # only the new query went through the encoder
+        s, i = ranker.top_k("alpha query", texts[:100], k=7)
+        assert store.h2d_rows == len(texts)
+        C = np.stack([table[t] for t in texts[:100]])
+        want = ro.cosine_topk_ref(table["alpha query"][None, :], C, 7)
+        np.testing.assert_array_equal(i, want[1][0])
+        np.testing.assert_allclose(s, want[0][0], atol=1e-5, rtol=0)
+        # the host view of the cache keeps the reference's contract
+        got = ranker.get_chunk_embeddings_batch(texts[5:9] + texts[5:6])
+        np.testing.assert_array_equal(got, np.stack([table[t] for t in texts[5:9] + texts[5:6]]))
+        fresh = R.OptimizedRanker(model_name="m", device_preference="cuda", cache_size=100000)
+        again = fresh.rank_single_query_optimized("beta query", df.iloc[::-1].reset_index(drop=True))
+        pd.testing.assert_frame_equal(second, again)
+        assert first.shape == second.shape
+    finally:
+        emb.set_embedding_backend(None)
+
+
+def test_device_row_store_eviction_and_cuda_encoder_handoff():
+    """The oldest quarter leaves when the cache overflows (reference :131-139), evicted chunks are re-encoded on demand, and
+    an encoder that returns CUDA tensors never touches the host link."""
+    from semanticsearch_b200.Tool import Sentence_Embedding as emb
+    R, ranker, texts, table, calls = _ranker_with_table(n=64, cuda_encoder=True)
+    try:
+        ranker.cache_size = ranker.chunk_embedding_cache.cache_size = 40
+        rows = ranker.get_chunk_embeddings_device(texts)             # 64 > 40: 16 oldest evicted after the gather
+        store = ranker.chunk_embedding_cache
+        assert rows.is_cuda and rows.shape == (64, 48) and len(store) == 48 and store.h2d_rows == 0 and store.d2d_rows == 64
+        np.testing.assert_array_equal(rows.cpu().numpy(), np.stack([table[t] for t in texts]))
+        n_calls = len(calls)
+        again = ranker.get_chunk_embeddings_device(texts[:20])        # 16 evicted chunks come back through the encoder
+        assert calls[n_calls:] == [texts[:16]]
+        np.testing.assert_array_equal(again.cpu().numpy(), np.stack([table[t] for t in texts[:20]]))
+    finally:
+        emb.set_embedding_backend(None)
+
+
+def test_one_poisoned_group_does_not_drop_the_block():
+    """a group whose encoding fails is reported and skipped; the other groups of the block are still ranked
+    (reference :488-536 isolates every query); a device failure propagates instead."""
+    from semanticsearch_b200 import _lib
+    from semanticsearch_b200.Tool import Sentence_Embedding as emb
+    R, ranker, texts, table, calls = _ranker_with_table(n=40)
+    try:
+        rows = []
+        for qid, qtext in ((1, "alpha query"), (2, "beta query"), (3, "alpha query")):
+            for j in range(10):
+                t = texts[(qid - 1) * 10 + j]
+                rows.append({"query_id": qid, "query_text": qtext, "chunk_id": f"c{qid}_{j}", "chunk_text": "poison" if (qid == 2 and j == 3) else t})
+        df = pd.DataFrame(rows)
+        kept = R._process_queries_sequential(df, "m", 80, 20)
+        got_qids = sorted({int(k["query_id"].iloc[0]) for k in kept})
+        assert got_qids == [1, 3]                      # group 2 failed alone
+        for k in kept:
+            assert set(k["label"]) <= {0, 1} and len(k) >= 2
+
+        def broken(*a, **kw):
+            raise _lib.DeviceError("simulated kernel failure")
+        orig = R.rank_query_groups_batched
+        R.rank_query_groups_batched = broken
+        try:
+            with pytest.raises(_lib.DeviceError):
+                R._process_queries_sequential(df[df["query_id"] != 2], "m", 80, 20)
+        finally:
+            R.rank_query_groups_batched = orig
+    finally:
+        emb.set_embedding_backend(None)
+
+
+@pytest.mark.parametrize("algo,dtype,b", [("stream", torch.float32, 1), ("stream", torch.bfloat16, 3), ("tcstream", torch.bfloat16, 4),
+                                          ("gemm", torch.bfloat16, 130), ("small", torch.float32, 12)])
+def test_k_larger_than_the_corpus_pads_consistently(algo, dtype, b):
+    """k > n_rows returns the n real rows, then score -inf / index -1 / key 0 on every kernel path."""
+    from semanticsearch_b200 import similarity
+    g = torch.Generator(device="cuda").manual_seed(3)
+    C = torch.randn((6, 64), generator=g, device="cuda").to(dtype)
+    Q = torch.randn((b, 64), generator=g, device="cuda").to(dtype)
+    s, i, keys = similarity.cosine_topk(C, Q, 10, algo=algo, return_keys=True)
+    assert s.shape == (b, 10) and bool((i[:, 6:] == -1).all()) and bool(torch.isinf(s[:, 6:]).all()) and bool((keys[:, 6:] == 0).all())
+    want = ro.cosine_topk_ref(Q.float().cpu().numpy(), C.float().cpu().numpy(), 6)
+    np.testing.assert_array_equal(i[:, :6].cpu().numpy(), want[1])

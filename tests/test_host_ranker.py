@@ -76,14 +76,25 @@ def test_label_group_percentile_rule():
 
 
 def test_chunk_cache_drops_the_oldest_quarter():
-    """Reference :131-139."""
+    """Reference :131-139, on the bookkeeping of the device row store (md5 -> slot; the rows themselves live in HBM)."""
     r = R.OptimizedRanker(cache_size=8)
+    store = r.chunk_embedding_cache
     for i in range(9):
-        r.chunk_embedding_cache[f"k{i}"] = np.zeros(2, np.float32)
+        store.slots[f"k{i}"] = i
     r._manage_cache_size()
-    assert list(r.chunk_embedding_cache) == [f"k{i}" for i in range(2, 9)]   # 9 // 4 = 2 oldest entries evicted
+    assert list(store.keys()) == [f"k{i}" for i in range(2, 9)]   # 9 // 4 = 2 oldest entries evicted
+    assert sorted(store.free) == [0, 1]                            # their slots are reusable
     r._manage_cache_size()
-    assert len(r.chunk_embedding_cache) == 7                                   # at or under the limit: untouched
+    assert len(store) == 7 and "k2" in store and "k0" not in store  # at or under the limit: untouched
+
+
+def test_bm25_float64_order_survives_the_fp32_rank_keys():
+    """BM25 scores that differ below fp32 resolution keep their float64 order (reference :226-235 ranks float64 values)."""
+    scores = np.array([1.0, 1.0 + 1e-12, 1.0 - 1e-12, 0.5, 1.0 + 1e-12, 0.0])
+    key = R._f64_rank_surrogate(scores)
+    assert key.dtype == np.float32
+    order = np.lexsort((np.arange(len(key)), -key.astype(np.float64)))
+    assert list(order) == list(np.argsort(-scores, kind="stable")) == [1, 4, 0, 2, 3, 5]
 
 
 def test_column_aliases_and_memory_estimate(tmp_path):
