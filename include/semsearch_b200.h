@@ -275,7 +275,7 @@ int ss_c99_rank_matrix(const float* S, const int32_t* offsets, const int64_t* s_
  * int64[n_docs] start of each table, device).  min_chunk / max_cuts: per-document int32 arrays (device) or
  * null to use the *_all scalars (max_cuts < 0 = unlimited).  out_cuts[offsets[d] + i] = i-th picked cut of
  * document d, out_n_cuts[d] = count (0 when n < 2 * min_chunk, :165-166; -1 = min_chunk < 1), out_profile
- * (nullable) [offsets[d] + i] = inside density after i cuts (D_series, :206,234).  max_doc_rows <= 2048. */
+ * (nullable) [offsets[d] + i] = inside density after i cuts (D_series, :206,234).  max_doc_rows <= 4096. */
 int ss_c99_divisive_cuts(const float* R, const int32_t* offsets, const int64_t* s_offsets, const int64_t* sat_offsets,
                          int n_docs, int max_doc_rows, const int32_t* min_chunk, int min_chunk_all, const int32_t* max_cuts,
                          int max_cuts_all, double min_gain, int stop_by_gain, double* sat_workspace, int32_t* out_cuts,

@@ -9,7 +9,7 @@ breakpoints" has no counterpart in the reference; it is pinn
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -190,3 +190,70 @@ def c99_profile_knee_ref(picked, series, knee_c: float = 1.2, smooth_window: int
         if v < limit:
             return sorted(set(picked[: min(max(1, i) - 1, len(picked))]))
     return sorted(set(picked))
+
+
+# ---- float64 statement of the divisive search (exact block sums from a summed-area table): what the device kernel
+# ---- K10 must reproduce bit for bit; the reference itself compares fp32 ndarray.mean() values (c99_divisive_ref above)
+class BlockSumsF64:
+    """Summed-area table over the rank matrix: any square block sum in O(1)."""
+
+    def __init__(self, R: np.ndarray):
+        n = R.shape[0]
+        self.sat = np.zeros((n + 1, n + 1), dtype=np.float64)
+        self.sat[1:, 1:] = np.cumsum(np.cumsum(R.astype(np.float64), axis=0), axis=1)
+
+    def mean(self, a: int, b: int, default: float = 0.0) -> float:
+        """Mean of R[a:b, a:b]; ``default`` for an empty block (reference :216-217)."""
+        if b <= a:
+            return default
+        s = self.sat
+        return float(s[b, b] - s[a, b] - s[b, a] + s[a, a]) / float((b - a) * (b - a))
+
+    def total(self, a: int, b: int) -> float:
+        s = self.sat
+        return float(s[b, b] - s[a, b] - s[b, a] + s[a, a])
+
+
+def c99_divisive_f64_ref(R: np.ndarray, min_chunk: int, max_cuts: Optional[int], min_gain: float, stopping: str, knee_c: float,
+                   smooth_window: int) -> List[int]:
+    """Reference :194-264 — repeatedly take the cut with the largest inside-density gain."""
+    n = R.shape[0]
+    blocks = BlockSumsF64(R)
+    segs: List[Tuple[int, int]] = [(0, n)]
+    cuts: List[int] = []
+
+    def inside_density(segments) -> float:
+        tot, area = 0.0, 0
+        for a, b in segments:
+            if b <= a:
+                continue
+            tot += blocks.total(a, b)
+            area += (b - a) * (b - a)
+        return tot / float(area) if area > 0 else 0.0
+
+    profile = [inside_density(segs)]
+    by_gain = stopping.lower() == "gain"
+    while True:
+        best_gain, best_pos, best_idx, best_mean_all = -1e9, None, None, 0.0
+        for idx, (a, b) in enumerate(segs):
+            if (b - a) < 2 * min_chunk:
+                continue
+            mean_all = blocks.mean(a, b)
+            for c in range(a + min_chunk, b - min_chunk + 1):
+                gain = 0.5 * (blocks.mean(a, c, mean_all) + blocks.mean(c, b, mean_all)) - mean_all
+                if gain > best_gain:
+                    best_gain, best_pos, best_idx, best_mean_all = gain, c, idx, mean_all
+        thr = max(float(min_gain), 0.1 * abs(best_mean_all))
+        if best_pos is None or (max_cuts is not None and len(cuts) >= int(max_cuts)):
+            break
+        if by_gain and best_gain < thr:
+            break
+        a, b = segs.pop(int(best_idx))
+        segs += [(a, best_pos), (best_pos, b)]
+        cuts.append(int(best_pos))
+        profile.append(inside_density(sorted(segs)))
+    if stopping.lower() != "profile" or not cuts:
+        return sorted(set(cuts))
+    return c99_profile_knee_ref(cuts, profile, knee_c, smooth_window)
+
+

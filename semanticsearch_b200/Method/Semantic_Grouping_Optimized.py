@@ -25,7 +25,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from ..Tool import Sentence_Segmenter as _segmenter
-from .semantic_common import embed_sentences_batched, log_msg, normalize_device
+from .semantic_common import embed_sentences_batched, log_msg, normalize_device, pack_document_rows
 
 _HEADER_RE = re.compile(r"\s*[\"“”']{0,3}\s*Language:\s*\w+\s+Article\s*Type:\s*[A-Za-z0-9\-]+\.?\s*", re.IGNORECASE)
 
@@ -73,9 +73,8 @@ def device_pass_batch(doc_embeddings: Sequence[np.ndarray], tau: float = 0.15, k
     out: List[Optional[DevicePass]] = [None] * len(sizes)
     if not live:
         return out
-    rows = [np.ascontiguousarray(doc_embeddings[d], dtype=np.float32) for d in live]
-    plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
-    E = torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
+    plan = ragged.make_plan([sizes[d] for d in live], "cuda")
+    E = pack_document_rows([doc_embeddings[d] for d in live])   # host arrays or CUDA tensors straight from the encoder
     S = ragged.segmented_simmatrix(E, plan)
     res = ragged.group_threshold_pass(S, plan, tau=tau, knn_mode=knn_mode, symmetric=True)   # K3's S is bit-symmetric
     S_h = S.cpu().numpy()
@@ -560,7 +559,7 @@ def group_documents(docs: Sequence[Tuple[str, List[str], np.ndarray]], *, collec
     whole batch, then the host stage per document."""
     auto_params = bool(params.pop("auto_params", True))
     tau = 0.15 if sigmoid_tau_group is None else float(sigmoid_tau_group)
-    passes = device_pass_batch([np.asarray(e, dtype=np.float32) for _, _, e in docs], tau=tau,
+    passes = device_pass_batch([e for _, _, e in docs], tau=tau,
                                knn_mode=_knn_mode(auto_params, params.get("knn_k")))
     out = {}
     for (doc_id, sentences, _), dp in zip(docs, passes):

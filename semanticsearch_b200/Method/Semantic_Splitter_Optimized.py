@@ -26,7 +26,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from ..Tool import Sentence_Segmenter as _segmenter
-from .semantic_common import embed_sentences_batched, normalize_device
+from .semantic_common import embed_sentences_batched, normalize_device, pack_document_rows
 
 
 def extract_sentences_spacy(text: str) -> List[str]:
@@ -78,9 +78,8 @@ def splitter_device_pass(doc_embeddings: Sequence[np.ndarray], pct: float = 95.0
     out = [None] * len(sizes)
     if not live:
         return out
-    rows = [np.ascontiguousarray(doc_embeddings[d], dtype=np.float32) for d in live]
-    plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
-    E = torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
+    plan = ragged.make_plan([sizes[d] for d in live], "cuda")
+    E = pack_document_rows([doc_embeddings[d] for d in live])   # host arrays or CUDA tensors straight from the encoder
     adj = ragged.adjacent_cosine(E)
     thr, flags, stats, smooth = ragged.segmented_percentile(adj, plan, pct, want_stats=True)
     adj_h, thr_h, flags_h = adj.cpu().numpy(), thr.cpu().numpy(), flags.cpu().numpy()
@@ -107,8 +106,7 @@ def c99_boundaries_batch(doc_embeddings: Sequence[np.ndarray], min_chunk_sizes, 
     """``_c99_boundaries`` (reference :155-264) for a batch of documents in three launches per slice: similarity
     matrices (K3), rank transform, divisive cut search (K10).  Only the picked cuts (and, for
     ``stopping='profile'``, the density profile) come back to the host.  ``min_chunk_sizes``: one int or one per
-    document.  Documents the device search does not take (more than 2048 sentences, ``min_chunk < 1``) run the
-    host statement of the same search on the device-computed rank matrix."""
+    document.  Documents of up to 4096 sentences are supported (the reference corpus's longest has 3939)."""
     import torch
     from .. import ragged
     n_docs = len(doc_embeddings)
@@ -119,15 +117,18 @@ def c99_boundaries_batch(doc_embeddings: Sequence[np.ndarray], min_chunk_sizes, 
     out: List[List[int]] = [[] for _ in range(n_docs)]
     if max_cuts is not None and int(max_cuts) <= 0:
         return out                                       # :225 stops before the first cut
-    live, slow = [], []
+    # min_chunk < 1 searches like min_chunk = 1: the extra candidate cuts of the reference (c = a and c = b, :212) have an
+    # empty side, whose block mean is NaN and never wins
+    mins = [max(1, m) for m in mins]
+    live = []
     for d, e in enumerate(doc_embeddings):
         n = int(e.shape[0])
         if n < 2 * mins[d]:
             continue                                     # :165-166
-        (live if (mins[d] >= 1 and n <= ragged.C99_CUTS_MAX_ROWS) else slow).append(d)
-    for d in slow:
-        R = _c99_rank_on_device(doc_embeddings[d], bool(use_local_rank), int(mask_size))
-        out[d] = _divisive_cuts(R, mins[d], max_cuts, float(min_gain), mode, float(knee_c), int(smooth_window))
+        if n > ragged.C99_CUTS_MAX_ROWS:
+            raise ValueError(f"document {d} has {n} sentences; the device cut search takes at most {ragged.C99_CUTS_MAX_ROWS} "
+                             "(there is no host fallback)")
+        live.append(d)
     start = 0
     while start < len(live):
         stop, used = start, 0
@@ -140,9 +141,8 @@ def c99_boundaries_batch(doc_embeddings: Sequence[np.ndarray], min_chunk_sizes, 
             stop += 1
         ids = live[start:stop]
         start = stop
-        rows = [np.ascontiguousarray(doc_embeddings[d], dtype=np.float32) for d in ids]
-        plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
-        E = torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
+        plan = ragged.make_plan([int(doc_embeddings[d].shape[0]) for d in ids], "cuda")
+        E = pack_document_rows([doc_embeddings[d] for d in ids])
         S = ragged.segmented_simmatrix(E, plan)
         R = ragged.c99_rank_matrix(S, plan, use_local_rank=bool(use_local_rank), mask_size=int(mask_size), symmetric=True)
         del S
@@ -162,83 +162,9 @@ def c99_boundaries_batch(doc_embeddings: Sequence[np.ndarray], min_chunk_sizes, 
     return out
 
 
-def _c99_rank_on_device(embs: np.ndarray, use_local_rank: bool, mask_size: int) -> np.ndarray:
-    import torch
-    from .. import ragged
-    plan = ragged.make_plan([embs.shape[0]], "cuda")
-    E = torch.from_numpy(np.ascontiguousarray(embs, dtype=np.float32)).cuda()
-    S = ragged.segmented_simmatrix(E, plan)
-    R = ragged.c99_rank_matrix(S, plan, use_local_rank=use_local_rank, mask_size=mask_size)
-    n = embs.shape[0]
-    return R.cpu().numpy().reshape(n, n)
-
-
 # ----------------------------------------------------------------------------------------------
 # Host logic
 # ----------------------------------------------------------------------------------------------
-class _BlockSums:
-    """Summed-area table over the rank matrix: any square block sum in O(1)."""
-
-    def __init__(self, R: np.ndarray):
-        n = R.shape[0]
-        self.sat = np.zeros((n + 1, n + 1), dtype=np.float64)
-        self.sat[1:, 1:] = np.cumsum(np.cumsum(R.astype(np.float64), axis=0), axis=1)
-
-    def mean(self, a: int, b: int, default: float = 0.0) -> float:
-        """Mean of R[a:b, a:b]; ``default`` for an empty block (reference :216-217)."""
-        if b <= a:
-            return default
-        s = self.sat
-        return float(s[b, b] - s[a, b] - s[b, a] + s[a, a]) / float((b - a) * (b - a))
-
-    def total(self, a: int, b: int) -> float:
-        s = self.sat
-        return float(s[b, b] - s[a, b] - s[b, a] + s[a, a])
-
-
-def _divisive_cuts(R: np.ndarray, min_chunk: int, max_cuts: Optional[int], min_gain: float, stopping: str, knee_c: float,
-                   smooth_window: int) -> List[int]:
-    """Reference :194-264 — repeatedly take the cut with the largest inside-density gain."""
-    n = R.shape[0]
-    blocks = _BlockSums(R)
-    segs: List[Tuple[int, int]] = [(0, n)]
-    cuts: List[int] = []
-
-    def inside_density(segments) -> float:
-        tot, area = 0.0, 0
-        for a, b in segments:
-            if b <= a:
-                continue
-            tot += blocks.total(a, b)
-            area += (b - a) * (b - a)
-        return tot / float(area) if area > 0 else 0.0
-
-    profile = [inside_density(segs)]
-    by_gain = stopping.lower() == "gain"
-    while True:
-        best_gain, best_pos, best_idx, best_mean_all = -1e9, None, None, 0.0
-        for idx, (a, b) in enumerate(segs):
-            if (b - a) < 2 * min_chunk:
-                continue
-            mean_all = blocks.mean(a, b)
-            for c in range(a + min_chunk, b - min_chunk + 1):
-                gain = 0.5 * (blocks.mean(a, c, mean_all) + blocks.mean(c, b, mean_all)) - mean_all
-                if gain > best_gain:
-                    best_gain, best_pos, best_idx, best_mean_all = gain, c, idx, mean_all
-        thr = max(float(min_gain), 0.1 * abs(best_mean_all))
-        if best_pos is None or (max_cuts is not None and len(cuts) >= int(max_cuts)):
-            break
-        if by_gain and best_gain < thr:
-            break
-        a, b = segs.pop(int(best_idx))
-        segs += [(a, best_pos), (best_pos, b)]
-        cuts.append(int(best_pos))
-        profile.append(inside_density(sorted(segs)))
-    if stopping.lower() != "profile" or not cuts:
-        return sorted(set(cuts))
-    return _profile_knee(cuts, profile, knee_c, smooth_window)
-
-
 def _profile_knee(cuts: List[int], profile, knee_c: float, smooth_window: int) -> List[int]:
     """Reference :239-264 — keep the cuts picked before the first sharp drop of the smoothed density increments."""
     deltas = np.diff(np.array(profile, dtype=float))

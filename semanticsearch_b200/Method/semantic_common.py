@@ -81,6 +81,17 @@ def embed_sentences_batched(sentences: List[str], model_name: str, base_batch_si
 
 # ---------------- Similarity matrix ---------------- #
 
+def pack_document_rows(docs: Sequence) -> "torch.Tensor":
+    """Concatenate per-document embedding matrices into one CUDA float32 ``[rows, dim]`` tensor.  Encoder outputs that
+    already live in HBM (``SentenceTransformer.encode(convert_to_tensor=True)``) are concatenated on the device — the
+    embedding hand-off of SURVEY.md section 8f rank 4, no numpy round trip (reference :107-114); host arrays take one H2D copy."""
+    import torch
+    if all(isinstance(e, torch.Tensor) and e.is_cuda for e in docs):
+        return torch.cat([e.to(torch.float32) for e in docs], dim=0).contiguous()
+    rows = [np.ascontiguousarray(e.detach().cpu().numpy() if isinstance(e, torch.Tensor) else e, dtype=np.float32) for e in docs]
+    return torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
+
+
 def similarity_matrices_from_embeddings(doc_embeddings: Sequence[np.ndarray]) -> List[Optional[np.ndarray]]:
     """Batched core of ``create_similarity_matrix``: one kernel launch for all documents.
 
@@ -95,18 +106,10 @@ def similarity_matrices_from_embeddings(doc_embeddings: Sequence[np.ndarray]) ->
     if not live:
         return out
     dim = int(doc_embeddings[live[0]].shape[1])
-    on_device = all(isinstance(doc_embeddings[d], torch.Tensor) and doc_embeddings[d].is_cuda for d in live)
-    if on_device:
-        # embedding hand-off: encoder outputs that already live in HBM
-        # (SentenceTransformer.encode(convert_to_tensor=True)) skip the numpy round trip of reference :107-114
-        rows = [doc_embeddings[d].to(torch.float32) for d in live]
-    else:
-        rows = [np.ascontiguousarray(doc_embeddings[d].cpu().numpy() if isinstance(doc_embeddings[d], torch.Tensor)
-                                     else doc_embeddings[d], dtype=np.float32) for d in live]
-    if any(r.shape[1] != dim for r in rows):
+    if any(int(doc_embeddings[d].shape[1]) != dim for d in live):
         raise ValueError("all documents of one batch must share the embedding dimension")
-    plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
-    E = torch.cat(rows, dim=0).contiguous() if on_device else torch.from_numpy(np.concatenate(rows, axis=0)).cuda()
+    plan = ragged.make_plan([sizes[d] for d in live], "cuda")
+    E = pack_document_rows([doc_embeddings[d] for d in live])
     S = ragged.segmented_simmatrix(E, plan).cpu().numpy()
     for slot, d in enumerate(live):
         n = sizes[d]

@@ -32,7 +32,7 @@ constexpr int kCutWarps = kCutThreads / 32;
 constexpr int kCutTile = 32 * 32;  // doubles per warp
 // tiles (64 KB, reused by the search) + column and row carries of the table sweep
 constexpr size_t cut_smem_bytes(int cpt) { return static_cast<size_t>(kCutWarps) * kCutTile * 8 + 2 * static_cast<size_t>(cpt) * kCutThreads * 8; }
-constexpr int kCutMaxRows = 2048;
+constexpr int kCutMaxRows = 4096;  // 16 candidate cuts per thread; the reference corpus's longest document has 3939 sentences
 
 struct CutParams {
   const float* R;
@@ -329,7 +329,7 @@ extern "C" int ss_c99_divisive_cuts(const float* R, const int32_t* offsets, cons
     return fail(SS_ERR_INVALID_ARG, "ss_c99_divisive_cuts: null pointer");
   if (n_docs <= 0 || max_doc_rows <= 0) return fail(SS_ERR_INVALID_ARG, "ss_c99_divisive_cuts: sizes must be positive");
   if (!min_chunk && min_chunk_all < 1) return fail(SS_ERR_INVALID_ARG, "ss_c99_divisive_cuts: min_chunk must be >= 1");
-  if (max_doc_rows > kCutMaxRows) return fail(SS_ERR_UNSUPPORTED, "ss_c99_divisive_cuts: documents longer than 2048 sentences are not supported");
+  if (max_doc_rows > kCutMaxRows) return fail(SS_ERR_UNSUPPORTED, "ss_c99_divisive_cuts: documents longer than 4096 sentences are not supported");
   CutParams p;
   p.R = R;
   p.offsets = offsets;
@@ -354,5 +354,6 @@ extern "C" int ss_c99_divisive_cuts(const float* R, const int32_t* offsets, cons
   };
   if (max_doc_rows <= 2 * kCutThreads) return launch(c99_divisive_kernel<2>, cut_smem_bytes(2));
   if (max_doc_rows <= 4 * kCutThreads) return launch(c99_divisive_kernel<4>, cut_smem_bytes(4));
-  return launch(c99_divisive_kernel<8>, cut_smem_bytes(8));
+  if (max_doc_rows <= 8 * kCutThreads) return launch(c99_divisive_kernel<8>, cut_smem_bytes(8));
+  return launch(c99_divisive_kernel<16>, cut_smem_bytes(16));
 }

@@ -315,7 +315,7 @@ def c99_rank_matrix(S: torch.Tensor, plan: RaggedPlan, use_local_rank: bool = Fa
     return R
 
 
-C99_CUTS_MAX_ROWS = 2048  # longest document the device cut search takes (ss_c99_divisive_cuts)
+C99_CUTS_MAX_ROWS = 4096  # longest document the device cut search takes (ss_c99_divisive_cuts)
 
 
 def c99_divisive_cuts(R: torch.Tensor, plan: RaggedPlan, min_chunk, max_cuts=None, min_gain: float = 0.01,

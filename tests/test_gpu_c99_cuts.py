@@ -42,7 +42,7 @@ def _assert_same_picks_up_to_near_ties(got, want, R, name):
     assert sorted(got) == sorted(want), name
     if got == want:
         return
-    blocks = SP._BlockSums(R)
+    blocks = spo.BlockSumsF64(R)
 
     def gain(bnds, c):
         a = max(x for x in bnds if x < c)
@@ -105,9 +105,10 @@ def test_batch_matches_oracle(mode, local):
         assert got[d] == want, (d, sizes[d], mins[d])
 
 
-@pytest.mark.parametrize("n,m", [(520, 6), (700, 9), (1500, 20), (2048, 30)])
+@pytest.mark.parametrize("n,m", [(520, 6), (700, 9), (1500, 20), (2048, 30), (2049, 40), (3939, 79)])
 def test_long_documents_bit_exact_against_float64_statement(n, m):
-    """Documents past 512 sentences (4 and 8 candidate positions per thread): cuts, pick order and profile
+    """Documents past 512 sentences (4, 8 and 16 candidate positions per thread; 3939 = the longest document of the reference
+    corpus, document_length_summary.json:17): cuts, pick order and profile
     equal the float64 summed-area host statement exactly."""
     from semanticsearch_b200 import ragged
     from semanticsearch_b200.Method import Semantic_Splitter_Optimized as SP
@@ -120,10 +121,10 @@ def test_long_documents_bit_exact_against_float64_statement(n, m):
         cuts_h, n_h, prof_h = cuts.cpu().numpy(), n_cuts.cpu().numpy(), prof.cpu().numpy()
         for d, mm in enumerate((m, 4)):
             Rd = _doc_block(Rh, plan, d)
-            blocks = SP._BlockSums(Rd)
+            blocks = spo.BlockSumsF64(Rd)
             base, cnt = int(plan.offsets[d]), int(n_h[d])
             picked = [int(x) for x in cuts_h[base:base + cnt]]
-            want = SP._divisive_cuts(Rd, mm, None, 0.01, mode, 1.2, 3)
+            want = spo.c99_divisive_f64_ref(Rd, mm, None, 0.01, mode, 1.2, 3)
             got = sorted(set(picked)) if mode == "gain" else SP._profile_knee(picked, prof_h[base:base + cnt + 1], 1.2, 3)
             assert got == want and cnt > 0
             # profile: exact replay of the host's ascending-segment sum

@@ -187,3 +187,21 @@ def test_similarity_matrices_accept_device_embeddings():
     for a, b in zip(host, dev):
         if a is not None:
             np.testing.assert_array_equal(a, b)
+
+
+def test_cuda_tensor_handoff_equals_host_arrays():
+    """Encoder outputs that already live in HBM feed the grouping, splitter and similarity passes without a host round trip
+     and give the same bits as the numpy call."""
+    from semanticsearch_b200.Method import Semantic_Grouping_Optimized as G
+    from semanticsearch_b200.Method import Semantic_Splitter_Optimized as SP
+    from semanticsearch_b200.Method import semantic_common as sc
+    rng = np.random.default_rng(77)
+    docs = [rng.standard_normal((n, 64)).astype(np.float32) for n in (9, 40, 130, 2)]
+    dev = [torch.from_numpy(e).cuda() for e in docs]
+    for a, b in zip(sc.similarity_matrices_from_embeddings(docs), sc.similarity_matrices_from_embeddings(dev)):
+        assert np.array_equal(a, b)
+    for a, b in zip(G.device_pass_batch(docs), G.device_pass_batch(dev)):
+        assert np.array_equal(a.sim_sharp, b.sim_sharp) and np.array_equal(a.knn_idx, b.knn_idx) and a.q80 == b.q80
+    for a, b in zip(SP.splitter_device_pass(docs), SP.splitter_device_pass(dev)):
+        assert a["adj_sims"] == b["adj_sims"] and a["p95_threshold"] == b["p95_threshold"]
+    assert SP.c99_boundaries_batch(docs, 3) == SP.c99_boundaries_batch(dev, 3)

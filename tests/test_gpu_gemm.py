@@ -119,3 +119,10 @@ def test_full_size_config4_properties():
     assert (i7 == i[:48]).float().mean().item() > 0.995 and torch.allclose(s7, s[:48], atol=2e-5)
     s1, i1 = similarity.cosine_topk(C, Q[:1].contiguous(), k, algo="stream")
     assert (i1 == i[:1]).float().mean().item() >= 0.9 and torch.allclose(s1, s[:1], atol=2e-5)
+    # independent oracle over ALL 10 M rows for 32 queries (planted and ordinary ones): a row that every kernel of this
+    # repo dropped would still be found here
+    from conftest import exhaustive_topk_check
+    pick = torch.cat([torch.arange(0, 16, device="cuda"), torch.arange(2000, 2016, device="cuda")])
+    exhaustive_topk_check(C, Q[pick], k, s[pick], i[pick], score_tol=2e-3)
+    exhaustive_topk_check(C, Q[:16], k, s7[:16], i7[:16], score_tol=2e-3)
+    exhaustive_topk_check(C, Q[:1], k, s1, i1, score_tol=2e-3)

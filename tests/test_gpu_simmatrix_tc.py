@@ -114,3 +114,31 @@ def test_tc_packed_windows_of_small_documents():
         np.testing.assert_allclose(blk, _fp64(rows[d]), atol=TOL, rtol=0)
     blk5 = Sh[plan.s_offsets[5]:plan.s_offsets[6]].reshape(sizes[5], sizes[5])
     assert np.all(blk5[0] == 0)
+
+
+@pytest.mark.parametrize("kind", ["all_positive", "near_duplicates", "alternating", "huge_dynamic_range"])
+def test_tc_worst_cases_at_d768_stay_inside_the_parity_bound(kind):
+    """The 3xTF32 error grows with the width and with |S| (the tensor core truncates when it accumulates): pin the worst
+    cases at the widest supported width, d = 768 — all-positive rows (every S near 1, every product of one sign),
+    near-duplicates, sign-alternating rows and a 2^20 dynamic range inside one row — under the 1e-5 bound of north_star."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(768)
+    n, d = 512, 768
+    if kind == "all_positive":
+        E = np.abs(rng.standard_normal((n, d))).astype(np.float32) + 0.5
+    elif kind == "near_duplicates":
+        base = rng.standard_normal((1, d)).astype(np.float32)
+        E = (base + 1e-3 * rng.standard_normal((n, d))).astype(np.float32)
+    elif kind == "alternating":
+        E = (np.abs(rng.standard_normal((n, d))) * np.where(np.arange(d) % 2 == 0, 1.0, -1.0)).astype(np.float32)
+    else:
+        E = (rng.standard_normal((n, d)) * np.exp2(rng.integers(-10, 11, size=(n, d)))).astype(np.float32)
+    plan = ragged.make_plan([n, 37], "cuda")
+    S = ragged.segmented_simmatrix(torch.from_numpy(np.concatenate([E, E[:37]])).cuda(), plan, algo="tc").cpu().numpy()
+    got = S[: n * n].reshape(n, n)
+    E64 = E.astype(np.float64)
+    E64 /= np.linalg.norm(E64, axis=1, keepdims=True)
+    err = float(np.abs(got - E64 @ E64.T).max())
+    print(f"{kind}: max |S - S_fp64| = {err:.3e}")
+    assert err <= 1e-5
+    assert np.array_equal(got, got.T)

@@ -107,3 +107,28 @@ def test_tcstream_config5_shard_properties():
     rs, ri = torch.topk(ref, k, dim=1)
     assert torch.allclose(rs, s, atol=2e-5)
     assert (ri == i).float().mean().item() > 0.99
+
+
+def test_config5_shard_full_length_against_exhaustive_oracle():
+    """One whole 8-way shard of BASELINE config 5 (12.5 M x 384 fp16, 16 queries, top-100) against the exact answer of a
+    chunked torch fp32 pass over every row (tests/conftest.py:exhaustive_topk_check), duplicates and a zero row included."""
+    from conftest import exhaustive_topk_check
+    from semanticsearch_b200 import similarity
+    free, _total = torch.cuda.mem_get_info()
+    if free < 16 * (1 << 30):
+        pytest.skip("needs ~12 GB of free HBM")
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n, d, b, k = 12_500_000, 384, 16, 100
+    C = torch.empty((n, d), dtype=torch.float16, device="cuda")
+    for a in range(0, n, 1 << 21):
+        e = min(n, a + (1 << 21))
+        C[a:e] = torch.randn((e - a, d), generator=g, device="cuda").half()
+    Q = torch.randn((b, d), generator=g, device="cuda").half()
+    C[5] = Q[0] * 0.25
+    C[n - 3] = C[5]            # duplicate of a winner at the far end: the lower index must come first
+    C[1234567] = 0
+    s, i = similarity.cosine_topk(C, Q, k)
+    assert similarity.choose_algo(C, Q, k) == "tcstream"
+    assert int(i[0, 0]) == 5 and int(i[0, 1]) == n - 3
+    assert torch.all(s[:, 1:] <= s[:, :-1])
+    exhaustive_topk_check(C, Q, k, s, i, score_tol=2e-3)

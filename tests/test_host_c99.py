@@ -23,7 +23,7 @@ def _cases(golden_dir):
 def test_float64_block_sum_search_reproduces_reference_boundaries(golden_dir):
     n_cases = 0
     for name, m, kw, R, _D in _cases(golden_dir):
-        got = SP._divisive_cuts(R, int(kw.get("min_chunk_size", 3)), kw.get("max_cuts"), float(kw.get("min_gain", 0.01)),
+        got = spo.c99_divisive_f64_ref(R, int(kw.get("min_chunk_size", 3)), kw.get("max_cuts"), float(kw.get("min_gain", 0.01)),
                                 kw.get("stopping", "gain"), float(kw.get("knee_c", 1.2)), int(kw.get("smooth_window", 3)))
         assert got == m["bounds"], name
         n_cases += 1
@@ -46,7 +46,7 @@ def test_profile_knee_matches_oracle_and_reference(golden_dir):
 def test_block_sums_table():
     rng = np.random.default_rng(1)
     R = rng.integers(0, 50, size=(23, 23)).astype(np.float32)
-    b = SP._BlockSums(R)
+    b = spo.BlockSumsF64(R)
     for a, c in ((0, 23), (3, 9), (22, 23), (5, 5)):
         assert b.total(a, c) == float(R[a:c, a:c].astype(np.float64).sum())
     assert b.mean(5, 5, default=7.5) == 7.5 and b.mean(3, 9) == float(R[3:9, 3:9].astype(np.float64).mean())
