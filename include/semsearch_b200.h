@@ -261,7 +261,8 @@ int ss_diameter_split(const float* S, const int32_t* offsets, const int64_t* s_o
  * (Method/Semantic_Splitter_Optimized.py:189-192) or the clipped mask_size x mask_size local rank
  * (:171-186) when bit 0 of use_local_rank is set.  Bit 1 (value 2, global mode only) promises that every S equals its
  * transpose bit for bit (true for the output of ss_segmented_simmatrix*): the column ranks are then taken as the
- * transposed row ranks.  workspace_rows: int32[total_rows] scratch. */
+ * transposed row ranks.  workspace_rows: int32[total_rows + total_rows / 16 + 2 * n_docs + 8] scratch (row -> document map, tile list
+ * of the local mode). */
 int ss_c99_rank_matrix(const float* S, const int32_t* offsets, const int64_t* s_offsets, int n_docs, int total_rows,
                        int max_doc_rows, int use_local_rank, int mask_size, int32_t* workspace_rows, float* out_R,
                        void* stream);

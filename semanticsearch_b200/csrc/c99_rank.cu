@@ -291,6 +291,92 @@ static int launch_rank_sorted(const float* S, const int32_t* offsets, const long
   return SS_OK;
 }
 
+// ---- local mode on shared-memory tiles --------------------------------------------------------------------
+// R[i][j] = #{(a, b) in the clipped (2H+1)^2 window : S[a][b] < S[i][j]} / window size (Splitter:171-186; the controller's default
+// preset, simple_chunk_controller.py:1451).  One CTA per 32 x 64 tile of one document: the tile and its halo are staged in
+// shared memory once (out-of-document entries are +inf and never count), warp w owns 8 adjacent columns, lane l row l.
+// For every window row a thread loads the 8 + 2H values its 8 outputs share and compares each against the centres it
+// belongs to: 25 shared-memory loads per output instead of 121 global ones, conflict-free (odd row pitch).
+constexpr int kLrRows = 32, kLrCols = 64, kLrCpt = 8, kLrThreads = 256;
+
+__global__ void c99_tile_list_kernel(const int* __restrict__ offsets, int n_docs, int* __restrict__ count, int2* __restrict__ list) {
+  const int doc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (doc >= n_docs) return;
+  const int n = offsets[doc + 1] - offsets[doc];
+  const int t = (n + kLrRows - 1) / kLrRows;
+  if (t <= 0) return;
+  const int base = atomicAdd(count, t);
+  for (int i = 0; i < t; ++i) list[base + i] = make_int2(doc, i);
+}
+
+template <int H>
+__global__ void __launch_bounds__(kLrThreads) c99_local_rank_kernel(const float* __restrict__ S_all, const int* __restrict__ offsets,
+                                                                    const long long* __restrict__ s_offsets,
+                                                                    const int* __restrict__ count, const int2* __restrict__ list,
+                                                                    float* __restrict__ R_all) {
+  constexpr int TR = kLrRows + 2 * H, LD = (kLrCols + 2 * H) | 1;
+  __shared__ float tile[TR * LD];
+  if (static_cast<int>(blockIdx.x) >= *count) return;
+  const int2 e = list[blockIdx.x];
+  const int doc = e.x;
+  const int n = offsets[doc + 1] - offsets[doc];
+  const int i_base = e.y * kLrRows, j_base = static_cast<int>(blockIdx.y) * kLrCols;
+  if (j_base >= n) return;
+  const float* S = S_all + s_offsets[doc];
+  float* R = R_all + s_offsets[doc];
+  for (int t = threadIdx.x; t < TR * (kLrCols + 2 * H); t += kLrThreads) {
+    const int a = t / (kLrCols + 2 * H), b = t - a * (kLrCols + 2 * H);
+    const int gi = i_base - H + a, gj = j_base - H + b;
+    tile[a * LD + b] = (gi >= 0 && gi < n && gj >= 0 && gj < n) ? S[static_cast<size_t>(gi) * n + gj] : INFINITY;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = i_base + lane, c0 = j_base + w * kLrCpt;
+  if (i >= n || c0 >= n) return;
+  float ctr[kLrCpt];
+  int cnt[kLrCpt];
+#pragma unroll
+  for (int m = 0; m < kLrCpt; ++m) {
+    ctr[m] = tile[(lane + H) * LD + w * kLrCpt + m + H];
+    cnt[m] = 0;
+  }
+#pragma unroll
+  for (int a = 0; a <= 2 * H; ++a) {
+    const float* row = tile + (lane + a) * LD + w * kLrCpt;
+    float v[kLrCpt + 2 * H];
+#pragma unroll
+    for (int k = 0; k < kLrCpt + 2 * H; ++k) v[k] = row[k];
+#pragma unroll
+    for (int m = 0; m < kLrCpt; ++m)
+#pragma unroll
+      for (int b = 0; b <= 2 * H; ++b) cnt[m] += (v[m + b] < ctr[m]) ? 1 : 0;
+  }
+  const int rows_in = min(n, i + H + 1) - max(0, i - H);
+#pragma unroll
+  for (int m = 0; m < kLrCpt; ++m) {
+    const int j = c0 + m;
+    if (j < n) {
+      const int denom = rows_in * (min(n, j + H + 1) - max(0, j - H));
+      R[static_cast<size_t>(i) * n + j] = static_cast<float>(static_cast<double>(cnt[m]) / static_cast<double>(denom > 0 ? denom : 1));
+    }
+  }
+}
+
+template <int H>
+static int launch_local_rank(const float* S, const int32_t* offsets, const long long* s_offsets, int n_docs, int total_rows,
+                             int max_doc_rows, int32_t* workspace, float* out_R, cudaStream_t st) {
+  int* count = workspace + total_rows;                       // after the row -> document map
+  int2* list = reinterpret_cast<int2*>(workspace + ((static_cast<size_t>(total_rows) + 3) & ~static_cast<size_t>(1)));  // 8-byte aligned
+  SS_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
+  c99_tile_list_kernel<<<(n_docs + 255) / 256, 256, 0, st>>>(offsets, n_docs, count, list);
+  SS_CUDA_CHECK(cudaGetLastError());
+  const unsigned int max_tiles = static_cast<unsigned int>((total_rows + kLrRows - 1) / kLrRows + n_docs);
+  dim3 grid(max_tiles, static_cast<unsigned int>((max_doc_rows + kLrCols - 1) / kLrCols));
+  c99_local_rank_kernel<H><<<grid, kLrThreads, 0, st>>>(S, offsets, s_offsets, count, list, out_R);
+  SS_CUDA_CHECK(cudaGetLastError());
+  return SS_OK;
+}
+
 __global__ void c99_row_doc_kernel(const int* __restrict__ offsets, int n_docs, int* __restrict__ row_doc) {
   const int doc = blockIdx.x;
   if (doc >= n_docs) return;
@@ -319,9 +405,22 @@ extern "C" int ss_c99_rank_matrix(const float* S, const int32_t* offsets, const 
     if (max_doc_rows <= 512) return launch_rank_sorted<16, 32>(S, offsets, so, workspace_rows, n_docs, total_rows, max_doc_rows, symmetric, out_R, st);
     return launch_rank_sorted<64, 8>(S, offsets, so, workspace_rows, n_docs, total_rows, max_doc_rows, symmetric, out_R, st);
   }
+  const int m = std::max(3, mask_size | 1);
+  if (use_local_rank && !getenv("SS_C99_RANK_COUNTING")) {
+    const long long* so = reinterpret_cast<const long long*>(s_offsets);
+    switch (m / 2) {  // the tiled kernel is compiled for the common window sizes (11 = the reference's default)
+      case 1: return launch_local_rank<1>(S, offsets, so, n_docs, total_rows, max_doc_rows, workspace_rows, out_R, st);
+      case 2: return launch_local_rank<2>(S, offsets, so, n_docs, total_rows, max_doc_rows, workspace_rows, out_R, st);
+      case 3: return launch_local_rank<3>(S, offsets, so, n_docs, total_rows, max_doc_rows, workspace_rows, out_R, st);
+      case 4: return launch_local_rank<4>(S, offsets, so, n_docs, total_rows, max_doc_rows, workspace_rows, out_R, st);
+      case 5: return launch_local_rank<5>(S, offsets, so, n_docs, total_rows, max_doc_rows, workspace_rows, out_R, st);
+      case 6: return launch_local_rank<6>(S, offsets, so, n_docs, total_rows, max_doc_rows, workspace_rows, out_R, st);
+      case 7: return launch_local_rank<7>(S, offsets, so, n_docs, total_rows, max_doc_rows, workspace_rows, out_R, st);
+      default: break;  // larger windows: the counting kernel below
+    }
+  }
   if (smem > 48 * 1024)
     SS_CUDA_CHECK(cudaFuncSetAttribute(c99_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int m = std::max(3, mask_size | 1);
   c99_rank_kernel<<<total_rows, 256, smem, st>>>(S, offsets, reinterpret_cast<const long long*>(s_offsets), workspace_rows,
                                                 use_local_rank ? 1 : 0, m / 2, out_R);
   SS_CUDA_CHECK(cudaGetLastError());

@@ -306,7 +306,7 @@ def c99_rank_matrix(S: torch.Tensor, plan: RaggedPlan, use_local_rank: bool = Fa
     lib = _lib.load()
     with torch.cuda.device(dev):
         R = torch.empty(plan.total_s, dtype=torch.float32, device=dev)
-        ws = torch.empty(max(plan.total_rows, 1), dtype=torch.int32, device=dev)
+        ws = torch.empty(plan.total_rows + plan.total_rows // 16 + 2 * plan.n_docs + 8, dtype=torch.int32, device=dev)
         st = lib.ss_c99_rank_matrix(S.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), plan.n_docs,
                                     plan.total_rows, max(plan.max_rows, 1),
                                     int(bool(use_local_rank)) | (2 if (symmetric and not use_local_rank) else 0), int(mask_size),
