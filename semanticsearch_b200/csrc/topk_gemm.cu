@@ -54,6 +54,7 @@ struct GemmParams {
   long long n_tiles;
   int tiles_per_chunk;
   int n_chunks;
+  int warm_chunks;  // the first warm_chunks chunks hold ONE tile each: the launch's cold thresholds cost one tile per CTA, not a chunk
   long long n_units;
   int stages;
   const float* inv_c;  // padded to a multiple of G_BN entries, NaN past n_rows (never selected)
@@ -84,6 +85,20 @@ __device__ __noinline__ float epi_list_insert(ScoreIdx* list, int k, float sc, i
   e.ix = c;
   list[j * G_EPI_THREADS] = e;
   return list[(k - 1) * G_EPI_THREADS].v;
+}
+
+// Tile range of a chunk.  The first `warm_chunks` chunks are single tiles: every unit of the first waves is short, so the
+// global lists hold useful thresholds (the k-th best of ~10 k rows per query) after ~0.1 ms instead of after the ~0.55 ms that
+// 8-tile units with cold thresholds take (profiles/r02_k2_trace_experiment.txt); the remaining chunks have tiles_per_chunk tiles.
+__device__ __forceinline__ void chunk_tiles(int chunk, int warm_chunks, int tiles_per_chunk, long long n_tiles, long long& t0, long long& t1) {
+  if (chunk < warm_chunks) {
+    t0 = chunk;
+    t1 = chunk + 1;
+  } else {
+    t0 = warm_chunks + static_cast<long long>(chunk - warm_chunks) * tiles_per_chunk;
+    t1 = t0 + tiles_per_chunk;
+  }
+  t1 = t1 < n_tiles ? t1 : n_tiles;
 }
 
 // Global per-query result list, shared by every unit of the launch: gtop[query][0..k) holds packed keys, best first.
@@ -198,8 +213,8 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         if (lane != 0) continue;
         const int chunk = static_cast<int>(u / p.n_qb), qb = static_cast<int>(u % p.n_qb) * CG + static_cast<int>(cta_rank);
-        const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
-        const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+        long long t0, t1;
+        chunk_tiles(chunk, p.warm_chunks, p.tiles_per_chunk, p.n_tiles, t0, t1);
         for (long long t = t0; t < t1; ++t) {
           // this tile's 256 corpus inverse norms (1 KB) ride the TMA engine too
           mbar_wait(&inv_empty[ia], ia_ph ^ 1u);
@@ -242,8 +257,8 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const uint32_t tiles_lo = smem_desc_lo(smem_u32(tiles));
     for (long long u = worker; cta_rank == 0 && u < p.n_units; u += n_workers) {
       const int chunk = static_cast<int>(u / p.n_qb);
-      const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
-      const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+      long long t0, t1;
+      chunk_tiles(chunk, p.warm_chunks, p.tiles_per_chunk, p.n_tiles, t0, t1);
       for (long long t = t0; t < t1; ++t) {
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -282,8 +297,8 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const uint32_t lead_tmem_empty1 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u;
     for (long long u = worker; u < p.n_units; u += n_workers) {
       const int chunk = static_cast<int>(u / p.n_qb), qb = static_cast<int>(u % p.n_qb) * CG + static_cast<int>(cta_rank);
-      const long long t0 = static_cast<long long>(chunk) * p.tiles_per_chunk;
-      const long long t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+      long long t0, t1;
+      chunk_tiles(chunk, p.warm_chunks, p.tiles_per_chunk, p.n_tiles, t0, t1);
       const int query = qb * G_BM + row;
       const float inv_q = query < p.n_queries ? p.inv_q[query] : 0.f;
       for (int j = 0; j < p.k; ++j) {
@@ -428,6 +443,7 @@ struct GemmPlan {
   long long n_tiles;
   int tiles_per_chunk;
   int n_chunks;
+  int warm_chunks;
 };
 
 // CTA pairs need cluster launches of 2 CTAs with ~212 KB of shared memory each to be schedulable on this
@@ -478,7 +494,11 @@ static GemmPlan make_gemm_plan(long long n_rows, int n_queries) {
   static const int min_tiles = getenv("SS_GEMM_MIN_TILES") ? std::max(1, atoi(getenv("SS_GEMM_MIN_TILES"))) : 8;
   n_chunks = std::min<long long>(n_chunks, std::max<long long>(1, g.n_tiles / min_tiles));  // at least ~min_tiles tiles per chunk
   g.tiles_per_chunk = static_cast<int>((g.n_tiles + n_chunks - 1) / n_chunks);
-  g.n_chunks = static_cast<int>((g.n_tiles + g.tiles_per_chunk - 1) / g.tiles_per_chunk);
+  // warm-up prefix of single-tile chunks (16 measured best on 0.3 M and 1.25 M-row shards, profiles/r02_k2_warm_sweep.txt)
+  static const int warm = getenv("SS_GEMM_WARM_TILES") ? std::max(0, atoi(getenv("SS_GEMM_WARM_TILES"))) : 16;
+  g.warm_chunks = g.tiles_per_chunk > 1 ? static_cast<int>(std::min<long long>(warm, g.n_tiles / 4)) : 0;
+  const long long rest = g.n_tiles - g.warm_chunks;
+  g.n_chunks = g.warm_chunks + static_cast<int>((rest + g.tiles_per_chunk - 1) / g.tiles_per_chunk);
   return g;
 }
 
@@ -558,6 +578,7 @@ static int cosine_topk_gemm_impl(const void* corpus, int64_t n_rows, int dim, in
   p.n_tiles = g.n_tiles;
   p.tiles_per_chunk = g.tiles_per_chunk;
   p.n_chunks = g.n_chunks;
+  p.warm_chunks = g.warm_chunks;
   p.n_units = static_cast<long long>(g.n_chunks) * g.n_qb;
   p.inv_c = inv_c;
   p.inv_gmax = inv_gmax;
