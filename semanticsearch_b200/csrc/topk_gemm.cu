@@ -65,26 +65,34 @@ struct GemmParams {
   int max_lead;    // a producer starts its j-th unit only when the slowest CTA has started its (j - max_lead)-th
 };
 
-// Per-thread top-k list in shared memory, entry j of epilogue thread e at list[j * 128 + e]
-// (conflict-free across a warp).  Sorted descending; strict '>' keeps the earlier (lower-index)
-// entry first among equal scores.  Precondition: sc > current k-th best.  Returns the new k-th best.
+// Per-thread top-k list in shared memory, entry j of epilogue thread e at list[j * 256 + e] (conflict-free across a
+// warp).  The list is UNSORTED: the thread remembers where its weakest entry sits (`min_pos`), a candidate that beats the
+// k-th best replaces that entry with one store, and one pass of k independent loads finds the new weakest entry
+// (score ascending, then row index descending, so that among equal scores the higher row leaves first and strict '>'
+// keeps the earlier, lower-index entry).  A sorted insertion costs a dependent load / compare / store chain per slot,
+// ~500 cycles per event in the cold phase of a launch, when every column passes in some lane of the warp; the global
+// lists take keys in any order, so nothing needs the sort.  Precondition: sc > current k-th best.  Returns the new one.
 struct ScoreIdx {
   float v;
   int ix;
 };
-__device__ __noinline__ float epi_list_insert(ScoreIdx* list, int k, float sc, int c) {
-  int j = k - 1;
-  while (j > 0) {
-    const ScoreIdx up = list[(j - 1) * G_EPI_THREADS];
-    if (!(sc > up.v)) break;
-    list[j * G_EPI_THREADS] = up;
-    --j;
-  }
+__device__ __noinline__ float epi_list_insert(ScoreIdx* list, int k, float sc, int c, int& min_pos) {
   ScoreIdx e;
   e.v = sc;
   e.ix = c;
-  list[j * G_EPI_THREADS] = e;
-  return list[(k - 1) * G_EPI_THREADS].v;
+  list[min_pos * G_EPI_THREADS] = e;
+  float mv = INFINITY;
+  int mi = -1, mp = 0;
+#pragma unroll 4
+  for (int j = 0; j < k; ++j) {
+    const ScoreIdx x = list[j * G_EPI_THREADS];
+    const bool weaker = x.v < mv || (x.v == mv && x.ix > mi);
+    mv = weaker ? x.v : mv;
+    mi = weaker ? x.ix : mi;
+    mp = weaker ? j : mp;
+  }
+  min_pos = mp;
+  return mv;
 }
 
 // Tile range of a chunk.  The first `warm_chunks` chunks are single tiles: every unit of the first waves is short, so the
@@ -120,7 +128,7 @@ __device__ __forceinline__ void publish_key(unsigned long long* g, int k, unsign
 // beat it unless max(raw dot) * max(1/|c| of the group) * 1/|q| does, which needs no per-column multiply;
 // the exact scores (raw * 1/|c| * 1/|q|) are formed only for the rare group that passes.
 __device__ __forceinline__ void epi_group(const uint32_t (&r)[32], const float* inv_grp, float gmax, float inv_q, float& thr,
-                                          float thr_floor, ScoreIdx* my_list, int k, int col0) {
+                                          float thr_floor, ScoreIdx* my_list, int& min_pos, int k, int col0) {
   float m = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 32; j += 4)
@@ -133,7 +141,7 @@ __device__ __forceinline__ void epi_group(const uint32_t (&r)[32], const float* 
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float sc = (__uint_as_float(r[j + e]) * ivs[e]) * inv_q;
-        if (sc > thr) thr = fmaxf(thr_floor, epi_list_insert(my_list, k, sc, col0 + j + e));
+        if (sc > thr) thr = fmaxf(thr_floor, epi_list_insert(my_list, k, sc, col0 + j + e, min_pos));
       }
     }
   }
@@ -307,6 +315,7 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         e.ix = -1;
         my_list[j * G_EPI_THREADS] = e;
       }
+      int min_pos = 0;  // every slot is empty: any of them is the weakest
       // Seed the threshold with the k-th best score published so far for this query (all units, all chunks): rows
       // scoring below it cannot reach the global top-k.  One step below: equal scores still compete on the row index.
       float thr = -INFINITY;
@@ -330,10 +339,10 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int c0 = 0; c0 < G_EPI_COLS; c0 += 64) {
           tmem_ld_wait();                                   // ra = columns c0 .. c0+31
           tmem_ld32(taddr + static_cast<uint32_t>(c0 + 32), rb);  // in flight while ra is processed
-          epi_group(ra, inv_tile + c0, gmax_tile[c0 >> 5], inv_q, thr, thr_floor, my_list, p.k, col_base + c0);
+          epi_group(ra, inv_tile + c0, gmax_tile[c0 >> 5], inv_q, thr, thr_floor, my_list, min_pos, p.k, col_base + c0);
           tmem_ld_wait();                                   // rb = columns c0+32 .. c0+63
           if (c0 + 64 < G_EPI_COLS) tmem_ld32(taddr + static_cast<uint32_t>(c0 + 64), ra);
-          epi_group(rb, inv_tile + c0 + 32, gmax_tile[(c0 >> 5) + 1], inv_q, thr, thr_floor, my_list, p.k, col_base + c0 + 32);
+          epi_group(rb, inv_tile + c0 + 32, gmax_tile[(c0 >> 5) + 1], inv_q, thr, thr_floor, my_list, min_pos, p.k, col_base + c0 + 32);
         }
         tc_fence_before();
         __syncwarp();
@@ -347,13 +356,16 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
       }
       if (query < p.n_queries) {
-        // publish what this unit found: the list is best-first, so the first entry that cannot enter ends the walk
+        // publish what this unit found (any order): only keys above the current global k-th best can enter
+        unsigned long long gk = *reinterpret_cast<volatile unsigned long long*>(gq + p.k - 1);
         for (int j = 0; j < p.k; ++j) {
           const ScoreIdx e = my_list[j * G_EPI_THREADS];
-          if (e.ix < 0) break;
+          if (e.ix < 0) continue;
           const unsigned long long key = make_key(e.v, p.index_base + static_cast<uint32_t>(e.ix));
-          if (key <= *reinterpret_cast<volatile unsigned long long*>(gq + p.k - 1)) break;
-          publish_key(gq, p.k, key);
+          if (key > gk) {
+            publish_key(gq, p.k, key);
+            gk = *reinterpret_cast<volatile unsigned long long*>(gq + p.k - 1);
+          }
         }
       }
     }
