@@ -98,6 +98,11 @@ def cfg1(steps=20, cpu=True):
     return out
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two config-2 kernels from the final-code ncu captures
+CFG2_TRAFFIC = {"k3": (20.030982e9 + 3.766918e9, "profiles/r02_k3_final_ncu_summary.txt"),
+                "k4": (8.571646e9 + 4.481500e9 + 0.117e9, "profiles/r02_cfg2_final_ncu_summary.txt")}
+
+
 def cfg2(steps=3, docs=10000, cpu=True, traffic=None):
     rng = np.random.default_rng(3)
     sizes = rng.integers(16, 513, size=docs)
@@ -111,8 +116,11 @@ def cfg2(steps=3, docs=10000, cpu=True, traffic=None):
     out = {"workload": f"cfg2: {docs} docs, n~U[16,512], 768-d fp32: S = En En^T + grouping threshold pass",
            "metric": "docs/s", "unit": "docs/s", "value": docs / ((ms_sim + ms_grp) * 1e-3), "ms_per_step": ms_sim + ms_grp,
            "ms_simmatrix": ms_sim, "ms_group_pass": ms_grp, "rows": plan.total_rows, "sum_n2": plan.total_s, "dtype": "f32 (3xTF32 products)",
-           "roofline": _roof("segmented_simmatrix_tc_kernel (tcgen05 kind::tf32, 3xTF32)", alg_sim, ms_sim, traffic=(traffic or {}).get("k3")),
-           "roofline_group_pass": _roof("group_threshold_kernel", alg_grp, ms_grp, traffic=(traffic or {}).get("k4")),
+           "roofline": _roof("segmented_simmatrix_tc_kernel (tcgen05: kind::tf32 main term + kind::f16 cross terms)", alg_sim, ms_sim,
+                             traffic=CFG2_TRAFFIC["k3"][0] if docs == 10000 else None,
+                             note="traffic from " + CFG2_TRAFFIC["k3"][1] + "; shared-memory / epilogue bound, not HBM bound"),
+           "roofline_group_pass": _roof("group_threshold_kernel", alg_grp, ms_grp, traffic=CFG2_TRAFFIC["k4"][0] if docs == 10000 else None,
+                                        note="traffic from " + CFG2_TRAFFIC["k4"][1] + "; instruction-issue bound (per-row selection)"),
            "roofline_whole_pass": _roof("K3 + K4", alg_sim + 4 * plan.total_s, ms_sim + ms_grp,
                                         note="SURVEY.md 8d floor: read E once, write S and sim_sharp once"),
            "gpu_launches": steps * 4}

@@ -199,12 +199,17 @@ int ss_segmented_simmatrix(const float* rows, int dim, const int32_t* offsets, c
  * upper-triangular tiles, every fp32 operand split on the fly into tf32 hi + lo and multiplied as
  * hi.hi + hi.lo + lo.hi with tcgen05.mma kind::tf32 (fp32 accumulation in TMEM), so |S - S_fp32| stays
  * ~1e-6, inside the 1e-5 parity bound that plain TF32 would miss by two orders of magnitude.  Needs
- * dim % 4 == 0 and 16-byte aligned rows.  ss_segmented_plan128_host (HOST pointers) lists the work units
+ * dim % 4 == 0 and 16-byte aligned rows.  The two cross terms run as fp16 MMAs on per-row power-of-two scaled copies (the
+ * scale comes from the row's first 32 elements); out_range_flag (device int32, nullable, caller-zeroed) is set to 1 when
+ * a later element of some row exceeded that scale by more than 2^14 and saturated — such a batch should be recomputed
+ * with ss_segmented_simmatrix (embeddings never do this; rows scaled over 12 orders of magnitude are fine).
+ * ss_segmented_plan128_host (HOST pointers) lists the work units
  * {doc, tile row, tile column, 0} (int32 x 4 each); call it with units_host = NULL to size the table. */
 int ss_segmented_plan128_host(const int32_t* offsets_host, int n_docs, int32_t* units_host, int64_t capacity_units,
                               int64_t* total_units);
 int ss_segmented_simmatrix_tc(const float* rows, int64_t total_rows, int dim, const int32_t* offsets,
-                              const int64_t* s_offsets, const int32_t* units, int64_t n_units, float* out_S, void* stream);
+                              const int64_t* s_offsets, const int32_t* units, int64_t n_units, float* out_S,
+                              int32_t* out_range_flag, void* stream);
 
 /* ---- K4: semantic-grouping threshold pass ------------------------------------------------------
  * Per document, from S (layout of K3): sim_sharp = sigmoid(((S-mu)/sigma)/tau) in fp32 with zero

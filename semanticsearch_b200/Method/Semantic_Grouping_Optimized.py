@@ -75,7 +75,7 @@ def device_pass_batch(doc_embeddings: Sequence[np.ndarray], tau: float = 0.15, k
         return out
     plan = ragged.make_plan([sizes[d] for d in live], "cuda")
     E = pack_document_rows([doc_embeddings[d] for d in live])   # host arrays or CUDA tensors straight from the encoder
-    S = ragged.segmented_simmatrix(E, plan)
+    S = ragged.segmented_simmatrix(E, plan, validate=True)   # the drop-ins copy results to the host anyway: one more word
     res = ragged.group_threshold_pass(S, plan, tau=tau, knn_mode=knn_mode, symmetric=True)   # K3's S is bit-symmetric
     S_h = S.cpu().numpy()
     sharp_h = res["sim_sharp"].cpu().numpy()

@@ -143,7 +143,7 @@ def c99_boundaries_batch(doc_embeddings: Sequence[np.ndarray], min_chunk_sizes, 
         start = stop
         plan = ragged.make_plan([int(doc_embeddings[d].shape[0]) for d in ids], "cuda")
         E = pack_document_rows([doc_embeddings[d] for d in ids])
-        S = ragged.segmented_simmatrix(E, plan)
+        S = ragged.segmented_simmatrix(E, plan, validate=True)
         R = ragged.c99_rank_matrix(S, plan, use_local_rank=bool(use_local_rank), mask_size=int(mask_size), symmetric=True)
         del S
         cuts, n_cuts, profile = ragged.c99_divisive_cuts(R, plan, [mins[d] for d in ids], max_cuts, float(min_gain),

@@ -110,7 +110,7 @@ def similarity_matrices_from_embeddings(doc_embeddings: Sequence[np.ndarray]) ->
         raise ValueError("all documents of one batch must share the embedding dimension")
     plan = ragged.make_plan([sizes[d] for d in live], "cuda")
     E = pack_document_rows([doc_embeddings[d] for d in live])
-    S = ragged.segmented_simmatrix(E, plan).cpu().numpy()
+    S = ragged.segmented_simmatrix(E, plan, validate=True).cpu().numpy()
     for slot, d in enumerate(live):
         n = sizes[d]
         out[d] = S[plan.s_offsets[slot]:plan.s_offsets[slot + 1]].reshape(n, n).copy()
@@ -145,7 +145,7 @@ def split_indices_by_diameter(doc_embeddings: Sequence[np.ndarray], threshold: f
         return out
     rows = [np.ascontiguousarray(doc_embeddings[d], dtype=np.float32) for d in live]
     plan = ragged.make_plan([r.shape[0] for r in rows], "cuda")
-    S = ragged.segmented_simmatrix(torch.from_numpy(np.concatenate(rows, axis=0)).cuda(), plan)
+    S = ragged.segmented_simmatrix(torch.from_numpy(np.concatenate(rows, axis=0)).cuda(), plan, validate=True)
     ends, n_spans, _ = ragged.diameter_split(S, plan, float(threshold))
     ends_h, n_h = ends.cpu().numpy(), n_spans.cpu().numpy()
     for slot, d in enumerate(live):

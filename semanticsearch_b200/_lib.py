@@ -59,7 +59,7 @@ _SIGNATURES = {
     "ss_segmented_plan_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int)]),
     "ss_segmented_simmatrix": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "ss_segmented_plan128_host": (c_int, [c_void_p, c_int, c_void_p, c_int64, POINTER(c_int64)]),
-    "ss_segmented_simmatrix_tc": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "ss_segmented_simmatrix_tc": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "ss_group_threshold_pass": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
     "ss_group_block_sums": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

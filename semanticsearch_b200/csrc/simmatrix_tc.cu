@@ -7,9 +7,19 @@
 // (data_process/simple_chunk_controller.py:614,682,743) for a whole ragged batch in one launch.
 //
 // Parity needs |S - S_ref| <= 1e-5, which rules out plain TF32/BF16 products (1e-3).  Every fp32
-// operand x is split on the fly into hi = tf32(x) (round-to-nearest) and lo = x - hi (exact), and
-// each K step issues three kind::tf32 MMAs: hi.hi + hi.lo + lo.hi; the dropped lo.lo term and the
-// truncation of lo are ~2^-21 relative per product.  fp32 accumulation happens in TMEM.
+// operand x is split on the fly into hi = x with the low 13 mantissa bits dropped (what the tensor core
+// reads of a kind::tf32 operand anyway: the raw plane IS the hi operand) and lo = x - hi (exact), and the
+// product is hi.hi + hi.lo + lo.hi.  The main term runs as kind::tf32 MMAs on the raw planes; the two
+// cross terms are 2^-10 of it, so fp16 copies of hi and lo (11-bit significands) carry them with a relative
+// error of 2^-21 per product, 2^-19 = 1.9e-6 for a whole dot product in the worst case: they run as
+// kind::f16 MMAs with K = 16 — half the tensor time and half the shared-memory operand bytes of tf32 cross
+// terms (bf16 copies would be range-safe but their 8-bit significand puts the worst case at 1.5e-5, past the
+// parity bound).  fp16's range is handled per row: the splitter of a row takes the exponent of the largest
+// magnitude among the 32 elements of the row's first K block that is not all zero (every CTA and both operand
+// roles see the same blocks, so the choice is consistent), stores hi * 2^-e and lo * 2^(12-e), and the epilogue multiplies the cross
+// accumulator by 2^(e_a + e_b - 12) — exact powers of two.  A later element more than 2^15 times that
+// magnitude saturates (cvt.satfinite) and raises `range_flag`; callers that validate recompute such a batch
+// with the fp32 FFMA kernel.  fp32 accumulation happens in TMEM.
 //
 // Work unit = one 128 x 128 upper-triangular tile (ti <= tj) of one document, listed in a host-built
 // unit table.  Persistent CTAs, 14 warps:
@@ -33,7 +43,7 @@ namespace ss {
 constexpr int S_BM = 128;
 constexpr int S_BK = 32;                    // fp32 elements per K block = one 128-byte swizzle atom
 constexpr int S_PLANE = S_BM * 128;         // 16 KB: 128 rows x 128 bytes
-constexpr int S_STAGE_BYTES = 4 * S_PLANE;  // A hi | B hi | A lo | B lo
+constexpr int S_STAGE_BYTES = 4 * S_PLANE;  // A raw | B raw | A fp16 {hi | lo} | B fp16 {hi | lo}
 constexpr int S_STAGES = 3;
 constexpr int S_THREADS = 14 * 32;
 constexpr int S_TMEM_COLS = 512;  // 2 buffers x (main accumulator | correction accumulator) x 128 columns
@@ -46,6 +56,7 @@ struct SimTcParams {
   int dim;
   int nkb;
   float* out;
+  int* range_flag;  // nullable: set to 1 when an element saturated its row's fp16 scale (see the header comment)
 };
 
 // Unit table entry {a, b, c, kind}.  kind 0: tile (ti = b, tj = c) of document a.  kind 1: a PACKED window —
@@ -108,7 +119,8 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
   unsigned char* tiles = smem;                                                       // [S_STAGES][64 KB]
   float* scratch = reinterpret_cast<float*>(tiles + S_STAGES * S_STAGE_BYTES);      // [4 warps][32][33] transpose staging
   float* inv_s = scratch + 4 * 32 * 33;                                              // [2][256]: 1/|row| of the A rows, then the B rows
-  long long* row_base_s = reinterpret_cast<long long*>(inv_s + 2 * 256);             // [128] per tile row: offset of (row, window col 0)
+  float* scale_s = inv_s + 2 * 256;                                                  // [2][256]: 2^(e - 6) of the A rows, then the B rows
+  long long* row_base_s = reinterpret_cast<long long*>(scale_s + 2 * 256);           // [128] per tile row: offset of (row, window col 0)
   int* row_lo = reinterpret_cast<int*>(row_base_s + 128);                             // [128] first / one-past-last window column it may write
   int* row_hi = row_lo + 128;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(row_hi + 128);
@@ -175,26 +187,29 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
       const bool diag = un.ti == un.tj;
       const int ncols = min(S_BM, un.n - un.tj * S_BM);
       const uint32_t idesc = make_idesc(2 /*tf32*/, S_BM, (ncols + 15) & ~15);
+      const uint32_t idesc_h = make_idesc(0 /*fp16*/, S_BM, (ncols + 15) & ~15);
       mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
       tc_fence_after();
       // The tensor core truncates when it adds into the fp32 accumulator, a bias that grows with the
       // number of accumulations at full magnitude.  The hi.hi products (96 MMAs at d = 768) therefore get
-      // an accumulator of their own; the 2 x 96 small cross terms go to a second one (their truncation
+      // an accumulator of their own; the small cross terms go to a second one (their truncation
       // error is ~1e-3 smaller) and the epilogue adds the two in fp32.
       const uint32_t d_main = tmem_base + static_cast<uint32_t>(acc * 2 * S_BM);
       const uint32_t d_corr = d_main + S_BM;
       for (int kb = 0; kb < p.nkb; ++kb) {
-        mbar_wait(&ready_bar[s], ph);  // hi / lo planes written and fenced by the splitters
+        mbar_wait(&ready_bar[s], ph);  // fp16 planes written and fenced by the splitters
         tc_fence_after();
         const uint32_t a_hi = tiles_lo + static_cast<uint32_t>(s) * (S_STAGE_BYTES >> 4);
         const uint32_t b_hi = diag ? a_hi : a_hi + (S_PLANE >> 4);
-        const uint32_t a_lo = a_hi + (2 * S_PLANE >> 4);
-        const uint32_t b_lo = diag ? a_lo : a_hi + (3 * S_PLANE >> 4);
+        const uint32_t a_cb = a_hi + (2 * S_PLANE >> 4);                 // row r: fp16 hi[0..32) | fp16 lo[0..32), both scaled
+        const uint32_t b_cb = diag ? a_cb : a_hi + (3 * S_PLANE >> 4);
 #pragma unroll
-        for (int k = 0; k < S_BK / 8; ++k) {  // K = 8 tf32 per MMA = 32 bytes = 2 descriptor units
+        for (int k = 0; k < S_BK / 8; ++k)  // K = 8 tf32 per MMA = 32 bytes = 2 descriptor units
           umma_tf32_lohi(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_tf32_lohi(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_tf32_lohi(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < S_BK / 16; ++k) {  // K = 16 fp16 per MMA = 32 bytes; the lo half of a row starts 64 bytes in
+          umma_f16_lohi<1>(d_corr, a_cb + 2 * k, b_cb + 4 + 2 * k, idesc_h, (kb | k) != 0 ? 1u : 0u);  // hi . lo
+          umma_f16_lohi<1>(d_corr, a_cb + 4 + 2 * k, b_cb + 2 * k, idesc_h, 1u);                        // lo . hi
         }
         umma_commit_elect<1>(&empty_bar[s]);
         if (kb == p.nkb - 1) umma_commit_elect<1>(&tmem_full[acc]);
@@ -229,23 +244,51 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
         active = (srow < 128 || e.y != e.z) && (blk * S_BM + r < n_doc);
       }
       float ssq0 = 0.f, ssq1 = 0.f;
+      float sc_hi = 1.f, sc_lo = 4096.f;  // 2^-e and 2^(12 - e) of this row, fixed at its first K block
+      int row_e = 0;
+      bool sat = false, have_scale = false;
       for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(&full_bar[s], ph);
         if (active) {
           unsigned char* base = tiles + s * S_STAGE_BYTES + plane_off + static_cast<uint32_t>(r) * 128u;
+          unsigned char* comb = base + 2 * S_PLANE;
+          const int sw = r & 7;  // SWIZZLE_128B: logical 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+          if (!have_scale) {
+            // the scale is fixed by the first K block that holds a normal number: the all-zero blocks before it convert
+            // to zeros under any scale, and every CTA that handles this row sees the same blocks in the same order
+            uint32_t mx = 0u;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = (j ^ (r & 7)) * 16;  // conflict-free: 8 consecutive rows touch 8 distinct 16-byte chunks
-            const float4 v = *reinterpret_cast<const float4*>(base + c);
-            // The tensor core reads a kind::tf32 operand through its upper 19 bits (sign, exponent, 10 mantissa bits): the raw
-            // plane IS the `hi` operand, hi = x with the low 13 bits dropped, and needs no rewrite.  lo = x - hi is exact in
-            // fp32 and is rounded to tf32 here (round-to-nearest, so the hardware's truncation of `lo` drops nothing).
-            float4 lo;
-            lo.x = tf32_rna(v.x - tf32_trunc(v.x)); lo.y = tf32_rna(v.y - tf32_trunc(v.y));
-            lo.z = tf32_rna(v.z - tf32_trunc(v.z)); lo.w = tf32_rna(v.w - tf32_trunc(v.w));
-            ssq0 = fmaf(v.x, v.x, fmaf(v.y, v.y, ssq0));
-            ssq1 = fmaf(v.z, v.z, fmaf(v.w, v.w, ssq1));
-            *reinterpret_cast<float4*>(base + 2 * S_PLANE + c) = lo;
+            for (int c = 0; c < 8; ++c) {
+              const uint4 w = *reinterpret_cast<const uint4*>(base + (c ^ sw) * 16);
+              mx = max(max(mx, w.x & 0x7FFFFFFFu), max(max(w.y & 0x7FFFFFFFu, w.z & 0x7FFFFFFFu), w.w & 0x7FFFFFFFu));
+            }
+            const int be = static_cast<int>(mx >> 23);  // biased exponent of the largest magnitude (0: zeros / denormals)
+            if (be != 0 && be != 255) {
+              have_scale = true;
+              row_e = min(max(be - 127, -100), 100);
+              sc_hi = __uint_as_float(static_cast<uint32_t>(127 - row_e) << 23);
+              sc_lo = __uint_as_float(static_cast<uint32_t>(127 + 12 - row_e) << 23);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {  // elements 8q .. 8q+7 of the row: raw chunks 2q, 2q+1 -> fp16 hi chunk q, lo chunk q + 4
+            // conflict-free: 8 consecutive rows touch 8 distinct 16-byte chunks in every access
+            const float4 v0 = *reinterpret_cast<const float4*>(base + ((2 * q) ^ sw) * 16);
+            const float4 v1 = *reinterpret_cast<const float4*>(base + ((2 * q + 1) ^ sw) * 16);
+            ssq0 = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, ssq0))));
+            ssq1 = fmaf(v0.z, v0.z, fmaf(v0.w, v0.w, fmaf(v1.z, v1.z, fmaf(v1.w, v1.w, ssq1))));
+            const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = x[2 * e] * sc_hi, b = x[2 * e + 1] * sc_hi;
+              sat |= fmaxf(fabsf(a), fabsf(b)) > 16000.f;  // lo * 2^12 reaches 4x the scaled hi: both must stay below 65504
+              const float la = (x[2 * e] - tf32_trunc(x[2 * e])) * sc_lo, lb = (x[2 * e + 1] - tf32_trunc(x[2 * e + 1])) * sc_lo;
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(b), "f"(a));    // cvt packs its FIRST source into the upper half: element 2e lands in the lower one
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l[e]) : "f"(lb), "f"(la));
+            }
+            *reinterpret_cast<uint4*>(comb + (q ^ sw) * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(comb + ((q + 4) ^ sw) * 16) = make_uint4(l[0], l[1], l[2], l[3]);
           }
           fence_proxy_async();  // generic-proxy writes above -> visible to the tensor core's async-proxy reads
         }
@@ -259,7 +302,11 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
       const float ssq = ssq0 + ssq1;
       mbar_wait(&norm_empty[acc], acc_ph ^ 1u);
       // zero rows stay zero (reference: norm 0 -> 1e-9, and 0 / 1e-9 == 0)
-      if (active) inv_s[acc * 256 + srow] = ssq > 0.f ? 1.0f / sqrtf(ssq) : 0.f;
+      if (active) {
+        inv_s[acc * 256 + srow] = ssq > 0.f ? 1.0f / sqrtf(ssq) : 0.f;
+        scale_s[acc * 256 + srow] = __uint_as_float(static_cast<uint32_t>(127 + row_e - 6) << 23);  // 2^(e - 6): a * b gives 2^(e_a + e_b - 12)
+        if (sat && p.range_flag != nullptr) *p.range_flag = 1;
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&norm_full[acc]);
       if (++acc == 2) {
@@ -314,6 +361,8 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
       const float* inv_a = inv_s + acc * 256;
       const float* inv_b = diag ? inv_a : inv_a + 128;
       const float my_inv = inv_a[row];
+      const float* scale_b = scale_s + acc * 256 + (diag ? 0 : 128);
+      const float my_scale = scale_s[acc * 256 + row];
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 2 * S_BM);
@@ -327,10 +376,11 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 ib = *reinterpret_cast<const float4*>(inv_b + c0 + j);
-            x[j] = (__uint_as_float(raw[j]) + __uint_as_float(cor[j])) * (my_inv * ib.x);
-            x[j + 1] = (__uint_as_float(raw[j + 1]) + __uint_as_float(cor[j + 1])) * (my_inv * ib.y);
-            x[j + 2] = (__uint_as_float(raw[j + 2]) + __uint_as_float(cor[j + 2])) * (my_inv * ib.z);
-            x[j + 3] = (__uint_as_float(raw[j + 3]) + __uint_as_float(cor[j + 3])) * (my_inv * ib.w);
+            const float4 sb = *reinterpret_cast<const float4*>(scale_b + c0 + j);
+            x[j] = fmaf(__uint_as_float(cor[j]), my_scale * sb.x, __uint_as_float(raw[j])) * (my_inv * ib.x);
+            x[j + 1] = fmaf(__uint_as_float(cor[j + 1]), my_scale * sb.y, __uint_as_float(raw[j + 1])) * (my_inv * ib.y);
+            x[j + 2] = fmaf(__uint_as_float(cor[j + 2]), my_scale * sb.z, __uint_as_float(raw[j + 2])) * (my_inv * ib.z);
+            x[j + 3] = fmaf(__uint_as_float(cor[j + 3]), my_scale * sb.w, __uint_as_float(raw[j + 3])) * (my_inv * ib.w);
           }
         }
         // transposed tile S[col][row]: lanes hold consecutive rows -> consecutive addresses.  Diagonal
@@ -433,7 +483,7 @@ extern "C" int ss_segmented_plan128_host(const int32_t* offsets_host, int n_docs
 
 extern "C" int ss_segmented_simmatrix_tc(const float* rows, int64_t total_rows, int dim, const int32_t* offsets,
                                          const int64_t* s_offsets, const int32_t* units, int64_t n_units, float* out_S,
-                                         void* stream) {
+                                         int32_t* out_range_flag, void* stream) {
   if (!rows || !offsets || !s_offsets || !units || !out_S) return fail(SS_ERR_INVALID_ARG, "ss_segmented_simmatrix_tc: null pointer");
   if (dim <= 0 || total_rows <= 0 || n_units < 0) return fail(SS_ERR_INVALID_ARG, "ss_segmented_simmatrix_tc: bad sizes");
   if (n_units == 0) return SS_OK;
@@ -453,7 +503,8 @@ extern "C" int ss_segmented_simmatrix_tc(const float* rows, int64_t total_rows, 
   p.dim = dim;
   p.nkb = (dim + S_BK - 1) / S_BK;
   p.out = out_S;
-  const size_t smem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + 4 * 32 * 33 * 4 + 2 * 256 * 4 + 128 * (8 + 4 + 4) + 256;
+  p.range_flag = out_range_flag;
+  const size_t smem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + 4 * 32 * 33 * 4 + 4 * 256 * 4 + 128 * (8 + 4 + 4) + 256;
   cudaError_t e = cudaFuncSetAttribute(segmented_simmatrix_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e == cudaSuccess) {
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(sm_count(), n_units)));

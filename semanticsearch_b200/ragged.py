@@ -83,11 +83,14 @@ def _units128(plan: RaggedPlan, dev) -> torch.Tensor:
     return plan.units128_d
 
 
-def segmented_simmatrix(E: torch.Tensor, plan: RaggedPlan, out: Optional[torch.Tensor] = None, algo: str = "auto") -> torch.Tensor:
+def segmented_simmatrix(E: torch.Tensor, plan: RaggedPlan, out: Optional[torch.Tensor] = None, algo: str = "auto",
+                        validate: bool = False) -> torch.Tensor:
     """All per-document ``S = En @ En.T`` blocks, packed (Method/semantic_common.py:158-191).
 
-    ``algo``: "tc" = tcgen05 3xTF32 kernel (needs dim % 4 == 0), "ffma" = CUDA-core fp32 kernel,
-    "auto" = "tc" whenever its layout constraints hold."""
+    ``algo``: "tc" = tcgen05 kernel (3-term split product, needs dim % 4 == 0), "ffma" = CUDA-core fp32 kernel,
+    "auto" = "tc" whenever its layout constraints hold.  The tensor-core kernel scales every row by a power of two taken
+    from its first 32 elements; ``validate=True`` reads back its range flag (one stream synchronisation) and recomputes the
+    batch with the fp32 kernel in the never-observed case that a later element of a row is > 2^14 times larger."""
     dev = _require_cuda(E)
     if E.dtype != torch.float32 or E.dim() != 2 or not E.is_contiguous():
         raise ValueError("E must be a contiguous float32 [total_rows, dim] tensor")
@@ -110,11 +113,13 @@ def segmented_simmatrix(E: torch.Tensor, plan: RaggedPlan, out: Optional[torch.T
             raise ValueError("out must be a CUDA float32 tensor with at least plan.total_s elements")
         if use_tc:
             units = _units128(plan, dev)
+            flag = torch.zeros(1, dtype=torch.int32, device=dev) if validate else None
             st = lib.ss_segmented_simmatrix_tc(E.data_ptr(), E.shape[0], E.shape[1], plan.offsets_d.data_ptr(),
                                                plan.s_offsets_d.data_ptr(), units.data_ptr(), units.shape[0], out.data_ptr(),
-                                               _stream_ptr(dev))
+                                               flag.data_ptr() if flag is not None else None, _stream_ptr(dev))
             _lib.check(st, "ss_segmented_simmatrix_tc")
-            return out
+            if flag is None or int(flag.item()) == 0:
+                return out
         st = lib.ss_segmented_simmatrix(E.data_ptr(), E.shape[1], plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(),
                                         plan.tile_prefix_d.data_ptr(), plan.n_docs, plan.total_tiles, out.data_ptr(),
                                         _stream_ptr(dev))

@@ -142,3 +142,43 @@ def test_tc_worst_cases_at_d768_stay_inside_the_parity_bound(kind):
     print(f"{kind}: max |S - S_fp64| = {err:.3e}")
     assert err <= 1e-5
     assert np.array_equal(got, got.T)
+
+
+def test_tc_row_scaling_of_the_fp16_cross_terms():
+    """The cross terms run on fp16 copies scaled per row by the exponent of the row's first 32 elements: rows whose first
+    block is tiny / huge / zero compared with the rest, and whole rows at 1e-12 ... 1e12, stay inside the parity bound; a
+    row with a later element > 2^14 times its first block raises the range flag and `validate=True` recomputes exactly."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(91)
+    n, d = 160, 384
+    E = rng.standard_normal((n, d)).astype(np.float32)
+    E[0, :32] *= 1e-3                      # first block 1000x smaller than the rest (still inside 2^14)
+    E[1, :32] *= 1e3                       # first block 1000x larger: the rest shrinks towards fp16's subnormals
+    E[2, :32] = 0.0                        # all-zero first block: scale 1
+    E[3] *= 1e-12                          # (fp32 sums of squares underflow below ~1e-19, in numpy too)
+    E[4] *= 1e12
+    E[5, :32] = 0.0
+    E[5] *= 1e-8                           # zero first block AND a tiny row
+    E[6] = np.abs(E[6]) * 3.0              # all positive
+    E[7] = E[6] * np.float32(1.5)          # parallel to row 6
+    plan = ragged.make_plan([n], "cuda")
+    Ed = torch.from_numpy(E).cuda()
+    S = ragged.segmented_simmatrix(Ed, plan, algo="tc", validate=True).cpu().numpy().reshape(n, n)
+    err = np.abs(S - _fp64(E))
+    print(f"row scaling: max |S - S_fp64| = {err.max():.3e} (rows 0-7: {err[:8].max():.3e})")
+    assert err.max() <= 1e-5
+    assert abs(S[6, 7] - 1.0) < 6e-6
+    # saturation: element 40 of row 9 is 1e6 times the row's first block
+    E2 = E.copy()
+    E2[9, 40] = 1e6
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    from semanticsearch_b200 import _lib
+    lib = _lib.load()
+    units = ragged._units128(plan, Ed.device)
+    E2d = torch.from_numpy(E2).cuda()
+    out = torch.empty(plan.total_s, dtype=torch.float32, device="cuda")
+    st = lib.ss_segmented_simmatrix_tc(E2d.data_ptr(), n, d, plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), units.data_ptr(),
+                                       units.shape[0], out.data_ptr(), flag.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert st == 0 and int(flag.item()) == 1
+    S2 = ragged.segmented_simmatrix(E2d, plan, algo="tc", validate=True).cpu().numpy().reshape(n, n)   # falls to the fp32 kernel
+    np.testing.assert_allclose(S2, _fp64(E2), atol=1e-5, rtol=0)
