@@ -211,7 +211,9 @@ cosine_topk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if (p.progress != nullptr) {
           ++j_unit;
           if (lane == 0) *reinterpret_cast<volatile int*>(p.progress + blockIdx.x) = j_unit;
-          for (;;) {
+          // The wait is a performance hint, never a dependency: it is bounded (~0.25 ms, several units), so a CTA whose
+          // siblings are not resident yet (another kernel holds their SMs) carries on instead of waiting for them.
+          for (int spins = 0; spins < 512; ++spins) {
             int mn = 0x7fffffff;
             for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) mn = min(mn, *reinterpret_cast<volatile int*>(p.progress + i));
             mn = __reduce_min_sync(0xffffffffu, mn);
