@@ -398,11 +398,24 @@ segmented_simmatrix_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, con
         for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = x[j];
         __syncwarp();
         const int c = c0 + lane;
+        if (!un.packed) {
+          // one document per tile: row j of this warp starts at an affine address, no per-row table look-ups
+          const int r0 = un.ti * S_BM + quad * 32;
+          const int rows_valid = un.n - r0;  // rows j < rows_valid lie inside the document
+          float* dst = p.out + un.s_off + static_cast<long long>(r0) * un.n + un.tj * S_BM + c;
+          const bool col_ok = c < ncols;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int rj = (warp - 2) * 32 + j;
-          const float y = scr[j * 33 + lane];
-          if (c >= row_lo[rj] && c < row_hi[rj] && (!diag || c >= quad * 32 + j)) p.out[row_base_s[rj] + c] = y;
+          for (int j = 0; j < 32; ++j) {
+            const float y = scr[j * 33 + lane];
+            if (col_ok && j < rows_valid && (!diag || c >= quad * 32 + j)) dst[static_cast<long long>(j) * un.n] = y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int rj = (warp - 2) * 32 + j;
+            const float y = scr[j * 33 + lane];
+            if (c >= row_lo[rj] && c < row_hi[rj] && (!diag || c >= quad * 32 + j)) p.out[row_base_s[rj] + c] = y;
+          }
         }
         __syncwarp();
       }
