@@ -529,6 +529,28 @@ def run_ours(args):
     main_res = describe(args.batch, args.steps, total_ms, kern_ms, e2e_ms, graph_ms) if rank == 0 else None
     verified = verify_search(corpus, q_dev, args.k, shard, lo, world, dev)
 
+    # Several GPUs: the ragged configs (2 and 3) under the same launch — documents partitioned over the ranks with a static
+    # LPT rule, no data-path collective, time = max over ranks.  Every rank takes part.
+    ragged_extra = None
+    default_shape = (args.rows, args.dim, args.k, args.dtype, args.batch) == (10_000_000, 768, 10, "bf16", 4096)
+    if world > 1 and default_shape and not args.no_extras:
+        del corpus, shard
+        graphed[0] = None
+        q_dev = q_host = None
+        torch.cuda.empty_cache()
+        import types
+        from benchmarks import bench_configs as _bc
+        ragged_extra = {}
+        for name, fn, kw in (("cfg2_sharded", _bc.config2, {"docs": 10000}), ("cfg3_sharded", _bc.config3, {"docs": 50000})):
+            try:
+                res = fn(types.SimpleNamespace(steps=3, realistic=False, rows=0, **kw))
+                res["n_gpus"] = world
+                res["partition"] = "static LPT over documents, no data-path collective; time = max over ranks"
+            except Exception as exc:  # noqa: BLE001
+                res = {"error": f"{type(exc).__name__}: {exc}"}
+            ragged_extra[name] = res
+            torch.cuda.empty_cache()
+
     if rank == 0:
         line = {
             "metric": metric_name(args), "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -541,7 +563,6 @@ def run_ours(args):
         line["verified"] = verified
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_reference_qps(args)
-        default_shape = (args.rows, args.dim, args.k, args.dtype, args.batch) == (10_000_000, 768, 10, "bf16", 4096)
         if world == 1 and not args.no_extras and (default_shape or args.extras):
             # BASELINE.json's other configs and the two 8f legs, each with value / roofline / cpu_baseline / e2e
             del corpus, shard
@@ -552,6 +573,8 @@ def run_ours(args):
             names = [n for n in args.extras.split(",") if n] or None
             more = _extras.run_all(names, cpu=not args.no_cpu_baseline, log=lambda m: print(m, file=sys.stderr))
             extra = dict(extra or {}, **more)
+        if ragged_extra:
+            extra = dict(extra or {}, **ragged_extra)
         if extra:
             line["extra"] = extra
         emit(line)

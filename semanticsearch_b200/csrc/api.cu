@@ -106,7 +106,7 @@ extern "C" int ss_profile_end(float* ms_out, int capacity, int* n_recorded, int*
   return SS_OK;
 }
 
-extern "C" int ss_version(void) { return 120; }
+extern "C" int ss_version(void) { return 200; }
 extern "C" const char* ss_last_error(void) { return ss::g_last_error.c_str(); }
 extern "C" int ss_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_per_block_optin) {
   const ss::DevInfo& d = ss::devinfo();
