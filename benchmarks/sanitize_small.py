@@ -35,10 +35,29 @@ E = rnd(sum(sizes), 100, torch.float32)
 plan = ragged.make_plan(sizes, "cuda")
 for algo in ("tc", "ffma"):
     S = ragged.segmented_simmatrix(E, plan, algo=algo)
+S = ragged.segmented_simmatrix(E, plan, algo="tc", validate=True)
 out = ragged.group_threshold_pass(S, plan)
+out_sym = ragged.group_threshold_pass(S, plan, symmetric=True)
+assert torch.equal(out["knn_idx"], out_sym["knn_idx"])
 ragged.similarity_distribution(S, plan)
-ragged.c99_rank_matrix(S, plan)
+R = ragged.c99_rank_matrix(S, plan)
+ragged.c99_rank_matrix(S, plan, symmetric=True)
+for mask in (3, 7, 11, 15, 21):                      # tiled local-rank kernel (H = 1..7) and the counting fallback
+    ragged.c99_rank_matrix(S, plan, use_local_rank=True, mask_size=mask)
+ragged.c99_divisive_cuts(R, plan, 3, want_profile=True)
 adj = ragged.adjacent_cosine(E)
 ragged.segmented_percentile(adj, plan, 95.0)
+# round-2 kernels: block sums / co-association, diameter split, long-document cut search, K2 with k = 16 and tiny corpora
+groups = [[list(range(0, n // 2)), list(range(n // 2, n)), [0, 0] if n else []] for n in sizes]
+ragged.group_block_sums(out["sim_sharp"], plan, groups)
+ragged.group_coassociation(np.random.default_rng(0).integers(0, 4, size=(5, 77)))
+ragged.diameter_split(S, plan, 0.4)
+big = [2100, 5]
+Eb = rnd(sum(big), 32, torch.float32)
+pb = ragged.make_plan(big, "cuda")
+Rb = ragged.c99_rank_matrix(ragged.segmented_simmatrix(Eb, pb), pb, symmetric=True)
+ragged.c99_divisive_cuts(Rb, pb, [40, 2])
+for n_small, b in ((300, 130), (6, 130), (257, 300)):
+    similarity.cosine_topk(rnd(n_small, 64, torch.bfloat16), rnd(b, 64, torch.bfloat16), 16 if n_small > 16 else 10, algo="gemm")
 torch.cuda.synchronize()
 print("sanitize_small: ok")
