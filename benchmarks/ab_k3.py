@@ -16,7 +16,6 @@ for n in names:
         fn = getattr(lib, fname, None)
         if fn is not None:
             fn.restype, fn.argtypes = restype, argtypes
-    lib._use_pairs = n.startswith("pair")
     libs[n] = lib
 mix = os.environ.get("AB_MIX", "cfg2")
 rng = np.random.default_rng(3)
@@ -31,15 +30,7 @@ S = torch.empty(plan.total_s, dtype=torch.float32, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 
 
-pairs_t = singles_t = None
-
-
 def k3(lib):
-    if getattr(lib, "_use_pairs", False):
-        rc = lib.ss_segmented_simmatrix_tc_pairs(E.data_ptr(), E.shape[0], E.shape[1], plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(),
-                                                 pairs_t.data_ptr(), pairs_t.shape[0], singles_t.data_ptr(), singles_t.shape[0], S.data_ptr(), None, st)
-        assert rc == 0, rc
-        return
     rc = lib.ss_segmented_simmatrix_tc(E.data_ptr(), E.shape[0], E.shape[1], plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(),
                                        units.data_ptr(), units.shape[0], S.data_ptr(), None, st)
     assert rc == 0, rc
