@@ -137,7 +137,9 @@ def cfg2(steps=3, docs=10000, cpu=True, traffic=None):
     d2h = sum(v.numel() * v.element_size() for v in holder["out"].values())
     out["e2e"] = {"value": docs / e2e_s, "unit": "docs/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": Eh.numel() * 4,
                   "d2h_bytes_per_step": d2h, "api": "ragged.grouping_pass_host (pinned host embeddings in, pinned host results out)",
-                  "note": "host-link bound: the step moves %.1f GB in and %.1f GB out" % (Eh.numel() * 4 / 1e9, d2h / 1e9)}
+                  "note": "host-link bound: the step moves %.1f GB in and %.1f GB out; document chunks are pipelined so that both "
+                          "directions of the link work at once (%.0f GB/s combined)" % (Eh.numel() * 4 / 1e9, d2h / 1e9,
+                                                                                       (Eh.numel() * 4 + d2h) / 1e9 / e2e_s)}
     if cpu:
         from oracle import grouping_oracle as go, simmatrix_oracle as so
         sample = list(range(0, docs, max(1, docs // 40)))[:40]

@@ -29,6 +29,7 @@ class RaggedPlan:
     s_offsets_d: torch.Tensor
     tile_prefix_d: torch.Tensor
     units128_d: Optional[torch.Tensor] = None   # int32 [units, 4] work list of the tensor-core kernel (built on first use)
+    host_chunks: Optional[tuple] = None         # grouping_pass_host's document chunks and their plans (built on first use)
 
     @property
     def n_docs(self) -> int:
@@ -128,7 +129,7 @@ def segmented_simmatrix(E: torch.Tensor, plan: RaggedPlan, out: Optional[torch.T
 
 
 def group_threshold_pass(S: torch.Tensor, plan: RaggedPlan, tau: float = 0.15, knn_mode: int = 0,
-                         symmetric: bool = False) -> Dict[str, torch.Tensor]:
+                         symmetric: bool = False, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """Grouping threshold pass for every document (Method/Semantic_Grouping_Optimized.py:100-115,
     270-283,343-360).  Returns device tensors: sim_sharp (packed), centrality [rows] f64,
     doc_stats [D,8] f64 = (mu, sigma, q80, q65, q60, 0.1*std, count, k), knn_idx/knn_val [rows,33].
@@ -139,11 +140,15 @@ def group_threshold_pass(S: torch.Tensor, plan: RaggedPlan, tau: float = 0.15, k
         raise ValueError("S must be the packed float32 output of segmented_simmatrix")
     lib = _lib.load()
     with torch.cuda.device(dev):
-        sharp = torch.empty(plan.total_s, dtype=torch.float32, device=dev)
-        cent = torch.empty(plan.total_rows, dtype=torch.float64, device=dev)
-        stats = torch.empty((plan.n_docs, 8), dtype=torch.float64, device=dev)
-        kidx = torch.empty((plan.total_rows, KNN_WIDTH), dtype=torch.int32, device=dev)
-        kval = torch.empty((plan.total_rows, KNN_WIDTH), dtype=torch.float32, device=dev)
+        if out is not None:   # caller-owned device buffers at least as large as this plan needs (grouping_pass_host's slots)
+            sharp, cent, stats = out["sim_sharp"][: plan.total_s], out["centrality"][: plan.total_rows], out["doc_stats"][: plan.n_docs]
+            kidx, kval = out["knn_idx"][: plan.total_rows], out["knn_val"][: plan.total_rows]
+        else:
+            sharp = torch.empty(plan.total_s, dtype=torch.float32, device=dev)
+            cent = torch.empty(plan.total_rows, dtype=torch.float64, device=dev)
+            stats = torch.empty((plan.n_docs, 8), dtype=torch.float64, device=dev)
+            kidx = torch.empty((plan.total_rows, KNN_WIDTH), dtype=torch.int32, device=dev)
+            kval = torch.empty((plan.total_rows, KNN_WIDTH), dtype=torch.float32, device=dev)
         st = lib.ss_group_threshold_pass(S.data_ptr(), plan.offsets_d.data_ptr(), plan.s_offsets_d.data_ptr(), plan.n_docs,
                                          float(tau), int(knn_mode), int(bool(symmetric)), sharp.data_ptr(), cent.data_ptr(), stats.data_ptr(),
                                          kidx.data_ptr(), kval.data_ptr(), _stream_ptr(dev))
@@ -448,23 +453,116 @@ def _to_host(tensors: Dict[str, torch.Tensor], out: Optional[Dict[str, torch.Ten
     return host
 
 
+_HOST_CHUNK_BYTES = 256 << 20   # embeddings + similarity matrix of one pipeline chunk of grouping_pass_host (128 MB ... 1.5 GB measured within 10 %)
+_side_streams: Dict[int, tuple] = {}
+
+
+def _copy_streams(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return _side_streams[key]
+
+
+def _host_chunks(plan: RaggedPlan, dim: int, chunk_bytes: int, dev):
+    """Contiguous document ranges of at most ``chunk_bytes`` of embeddings + similarity matrix each, with their own plans
+    (cached on the parent plan: a caller that reuses a plan pays for them once)."""
+    key = (dim, chunk_bytes)
+    if plan.host_chunks is not None and plan.host_chunks[0] == key:
+        return plan.host_chunks[1]
+    sizes = np.diff(plan.offsets).astype(np.int64)
+    cost = sizes * dim * 4 + sizes * sizes * 4
+    chunks, d0, acc = [], 0, 0
+    for d in range(plan.n_docs):
+        if d > d0 and acc + int(cost[d]) > chunk_bytes:
+            chunks.append((d0, d))
+            d0, acc = d, 0
+        acc += int(cost[d])
+    chunks.append((d0, plan.n_docs))
+    out = [(a, b, plan if len(chunks) == 1 else make_plan(sizes[a:b], dev)) for a, b in chunks]
+    plan.host_chunks = (key, out)
+    return out
+
+
 def grouping_pass_host(E_host: torch.Tensor, sizes: Sequence[int], tau: float = 0.15, knn_mode: int = 0,
-                       out: Optional[Dict[str, torch.Tensor]] = None, plan: Optional[RaggedPlan] = None) -> Dict[str, torch.Tensor]:
+                       out: Optional[Dict[str, torch.Tensor]] = None, plan: Optional[RaggedPlan] = None,
+                       chunk_bytes: int = _HOST_CHUNK_BYTES) -> Dict[str, torch.Tensor]:
     """``create_similarity_matrix`` + the grouping threshold pass (Method/semantic_common.py:158-191,
     Method/Semantic_Grouping_Optimized.py:100-115,270-283,351-355) for a packed batch of documents whose embeddings are
     in HOST memory: H2D copy, K3, K4, D2H copy of everything the host clustering stage reads (S, sim_sharp,
-    centrality, per-document thresholds, neighbour lists).  ``out``: the dict a previous call returned, to reuse its
-    pinned buffers.  The call synchronises before returning (the caller reads the results)."""
+    centrality, per-document thresholds, neighbour lists).  The step is bound by the host link — it returns about as
+    many bytes as it takes — so the batch runs as a pipeline of document chunks: the H2D copy of chunk i + 1, the
+    kernels of chunk i and the D2H copy of chunk i - 1 overlap (two copy streams, two device slots), which lets the two
+    directions of the link work at the same time.  ``out``: the dict a previous call returned, to reuse its pinned
+    buffers.  The call synchronises before returning (the caller reads the results)."""
     if E_host.is_cuda:
         raise ValueError("grouping_pass_host takes host embeddings (use segmented_simmatrix / group_threshold_pass for device tensors)")
     dev = torch.device("cuda", torch.cuda.current_device())
     plan = plan or make_plan(sizes, dev)
-    E = E_host.to(dev, non_blocking=True)
-    S = segmented_simmatrix(E, plan)
-    res = group_threshold_pass(S, plan, tau=tau, knn_mode=knn_mode, symmetric=True)   # K3 mirrors its tiles
-    res["S"] = S
-    host = _to_host(res, out)
-    torch.cuda.current_stream(dev).synchronize()
+    if E_host.dtype != torch.float32 or E_host.dim() != 2 or E_host.shape[0] != plan.total_rows:
+        raise ValueError("E_host must be a float32 [total_rows, dim] tensor matching the plan")
+    dim = E_host.shape[1]
+    chunks = _host_chunks(plan, dim, int(chunk_bytes), dev)
+    if len(chunks) == 1:
+        E = E_host.to(dev, non_blocking=True)
+        S = segmented_simmatrix(E, plan)
+        res = group_threshold_pass(S, plan, tau=tau, knn_mode=knn_mode, symmetric=True)   # K3 mirrors its tiles
+        res["S"] = S
+        host = _to_host(res, out)
+        torch.cuda.current_stream(dev).synchronize()
+        return host
+    shapes = {"S": ((plan.total_s,), torch.float32), "sim_sharp": ((plan.total_s,), torch.float32),
+              "centrality": ((plan.total_rows,), torch.float64), "doc_stats": ((plan.n_docs, 8), torch.float64),
+              "knn_idx": ((plan.total_rows, KNN_WIDTH), torch.int32), "knn_val": ((plan.total_rows, KNN_WIDTH), torch.float32)}
+    host = out if out is not None else {k: torch.empty(shp, dtype=dt, pin_memory=True) for k, (shp, dt) in shapes.items()}
+    max_rows = max(p.total_rows for _, _, p in chunks)
+    max_s = max(p.total_s for _, _, p in chunks)
+    max_docs = max(p.n_docs for _, _, p in chunks)
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = _copy_streams(dev)
+    slots = []
+    for _ in range(2):
+        slots.append({"E": torch.empty((max_rows, dim), dtype=torch.float32, device=dev),
+                      "S": torch.empty(max_s, dtype=torch.float32, device=dev),
+                      "sim_sharp": torch.empty(max_s, dtype=torch.float32, device=dev),
+                      "centrality": torch.empty(max_rows, dtype=torch.float64, device=dev),
+                      "doc_stats": torch.empty((max_docs, 8), dtype=torch.float64, device=dev),
+                      "knn_idx": torch.empty((max_rows, KNN_WIDTH), dtype=torch.int32, device=dev),
+                      "knn_val": torch.empty((max_rows, KNN_WIDTH), dtype=torch.float32, device=dev),
+                      "copied": torch.cuda.Event(), "computed": torch.cuda.Event(), "drained": torch.cuda.Event(), "used": False})
+    s_in.wait_stream(cur)    # the slots were allocated on the caller's stream
+    s_out.wait_stream(cur)
+    for i, (d0, d1, sub) in enumerate(chunks):
+        slot = slots[i & 1]
+        r0, r1 = int(plan.offsets[d0]), int(plan.offsets[d1])
+        e0, e1 = int(plan.s_offsets[d0]), int(plan.s_offsets[d1])
+        if r1 == r0:   # a chunk of empty documents
+            host["doc_stats"][d0:d1].zero_()
+            continue
+        if slot["used"]:
+            s_in.wait_event(slot["computed"])    # the kernels of chunk i - 2 have read this slot's embeddings
+        with torch.cuda.stream(s_in):
+            slot["E"][: r1 - r0].copy_(E_host[r0:r1], non_blocking=True)
+            slot["copied"].record(s_in)
+        cur.wait_event(slot["copied"])
+        if slot["used"]:
+            cur.wait_event(slot["drained"])      # ... and its results have left for the host
+        segmented_simmatrix(slot["E"][: r1 - r0], sub, out=slot["S"])
+        group_threshold_pass(slot["S"], sub, tau=tau, knn_mode=knn_mode, symmetric=True, out=slot)
+        slot["computed"].record(cur)
+        s_out.wait_event(slot["computed"])
+        with torch.cuda.stream(s_out):
+            host["S"][e0:e1].copy_(slot["S"][: e1 - e0], non_blocking=True)
+            host["sim_sharp"][e0:e1].copy_(slot["sim_sharp"][: e1 - e0], non_blocking=True)
+            host["centrality"][r0:r1].copy_(slot["centrality"][: r1 - r0], non_blocking=True)
+            host["doc_stats"][d0:d1].copy_(slot["doc_stats"][: d1 - d0], non_blocking=True)
+            host["knn_idx"][r0:r1].copy_(slot["knn_idx"][: r1 - r0], non_blocking=True)
+            host["knn_val"][r0:r1].copy_(slot["knn_val"][: r1 - r0], non_blocking=True)
+            slot["drained"].record(s_out)
+        slot["used"] = True
+    cur.wait_stream(s_out)
+    cur.wait_stream(s_in)
+    cur.synchronize()
     return host
 
 

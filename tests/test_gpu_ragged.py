@@ -323,3 +323,24 @@ def test_group_pass_heavy_ties_with_symmetric_promise():
         rows_d = slice(plan.offsets[d], plan.offsets[d + 1])
         np.testing.assert_array_equal(kidx[rows_d, :w], idx_ref)
         np.testing.assert_array_equal(kval[rows_d, :w], val_ref)
+
+
+def test_grouping_pass_host_pipeline_matches_the_single_pass():
+    """The host-buffer operator runs long batches as a pipeline of document chunks (H2D / kernels / D2H overlapped on two
+    copy streams): every output must equal the one-chunk pass bit for bit, including empty documents, chunk boundaries
+    that fall next to them, a reused plan and reused pinned output buffers."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(21)
+    sizes = [int(x) for x in rng.integers(1, 300, size=90)] + [0, 0, 513, 2, 0, 64, 65]
+    E = torch.from_numpy(rng.standard_normal((sum(sizes), 96)).astype(np.float32)).pin_memory()
+    one = ragged.grouping_pass_host(E, sizes, chunk_bytes=1 << 40)
+    one = {k: v.clone() for k, v in one.items()}
+    plan = ragged.make_plan(sizes, "cuda")
+    out = None
+    for _ in range(2):                                   # second round: cached chunk plans, reused pinned outputs
+        out = ragged.grouping_pass_host(E, sizes, out=out, plan=plan, chunk_bytes=1 << 20)
+        assert len(plan.host_chunks[1]) > 5
+        assert set(out) == set(one)
+        for k in one:
+            assert out[k].shape == one[k].shape and out[k].dtype == one[k].dtype, k
+            assert torch.equal(out[k].view(torch.uint8), one[k].view(torch.uint8)), k
