@@ -653,18 +653,66 @@ class SplitterStream:
 
 
 def c99_cuts_host(E_host: torch.Tensor, sizes: Sequence[int], min_chunk, use_local_rank: bool = False, mask_size: int = 11,
-                  min_gain: float = 0.01, plan: Optional[RaggedPlan] = None) -> Dict[str, torch.Tensor]:
+                  min_gain: float = 0.01, plan: Optional[RaggedPlan] = None, chunk_bytes: int = _HOST_CHUNK_BYTES) -> Dict[str, torch.Tensor]:
     """The C99 leg of the splitter (Method/Semantic_Splitter_Optimized.py:169-238) for a packed batch of documents in
     HOST memory: H2D, similarity matrices, rank transform (global, or the reference preset's 11 x 11 local rank,
-    data_process/simple_chunk_controller.py:1451), divisive cut search, D2H of the cuts."""
+    data_process/simple_chunk_controller.py:1451), divisive cut search, D2H of the cuts.  The step takes megabytes in per
+    byte out, so long batches run as document chunks whose H2D copy (a side stream, two device slots) overlaps the
+    kernels of the chunk before."""
     if E_host.is_cuda:
         raise ValueError("c99_cuts_host takes host embeddings")
     dev = torch.device("cuda", torch.cuda.current_device())
     plan = plan or make_plan(sizes, dev)
-    E = E_host.to(dev, non_blocking=True)
-    S = segmented_simmatrix(E, plan)
-    R = c99_rank_matrix(S, plan, use_local_rank=use_local_rank, mask_size=mask_size, symmetric=not use_local_rank)
-    cuts, n_cuts, _ = c99_divisive_cuts(R, plan, min_chunk, min_gain=min_gain)
+    if E_host.dtype != torch.float32 or E_host.dim() != 2 or E_host.shape[0] != plan.total_rows:
+        raise ValueError("E_host must be a float32 [total_rows, dim] tensor matching the plan")
+    chunks = _host_chunks(plan, E_host.shape[1], int(chunk_bytes), dev)
+    if len(chunks) == 1:
+        E = E_host.to(dev, non_blocking=True)
+        S = segmented_simmatrix(E, plan)
+        R = c99_rank_matrix(S, plan, use_local_rank=use_local_rank, mask_size=mask_size, symmetric=not use_local_rank)
+        cuts, n_cuts, _ = c99_divisive_cuts(R, plan, min_chunk, min_gain=min_gain)
+        host = _to_host({"cuts": cuts, "n_cuts": n_cuts})
+        torch.cuda.current_stream(dev).synchronize()
+        return host
+    per_doc_min = None if np.ndim(min_chunk) == 0 else np.ascontiguousarray(min_chunk, dtype=np.int32)
+    if per_doc_min is not None and per_doc_min.shape != (plan.n_docs,):
+        raise ValueError("min_chunk must be a scalar or one value per document")
+    cur = torch.cuda.current_stream(dev)
+    s_in, _ = _copy_streams(dev)
+    max_rows = max(p.total_rows for _, _, p in chunks)
+    slots = [{"E": torch.empty((max_rows, E_host.shape[1]), dtype=torch.float32, device=dev), "copied": torch.cuda.Event(),
+              "computed": torch.cuda.Event(), "used": False} for _ in range(2)]
+    cuts = torch.empty(plan.total_rows, dtype=torch.int32, device=dev)
+    n_cuts = torch.zeros(plan.n_docs, dtype=torch.int32, device=dev)
+    s_in.wait_stream(cur)
+
+    def load(i):
+        d0, d1, _ = chunks[i]
+        r0, r1 = int(plan.offsets[d0]), int(plan.offsets[d1])
+        slot = slots[i & 1]
+        if slot["used"]:
+            s_in.wait_event(slot["computed"])   # the kernels of chunk i - 2 have read this slot
+        with torch.cuda.stream(s_in):
+            if r1 > r0:
+                slot["E"][: r1 - r0].copy_(E_host[r0:r1], non_blocking=True)
+            slot["copied"].record(s_in)
+
+    load(0)
+    for i, (d0, d1, sub) in enumerate(chunks):
+        if i + 1 < len(chunks):
+            load(i + 1)                          # its copy runs under this chunk's kernels
+        slot = slots[i & 1]
+        r0, r1 = int(plan.offsets[d0]), int(plan.offsets[d1])
+        cur.wait_event(slot["copied"])
+        if r1 > r0:
+            S = segmented_simmatrix(slot["E"][: r1 - r0], sub)
+            R = c99_rank_matrix(S, sub, use_local_rank=use_local_rank, mask_size=mask_size, symmetric=not use_local_rank)
+            c, nc, _ = c99_divisive_cuts(R, sub, min_chunk if per_doc_min is None else per_doc_min[d0:d1], min_gain=min_gain)
+            cuts[r0:r1].copy_(c[: r1 - r0])
+            n_cuts[d0:d1].copy_(nc)
+        slot["computed"].record(cur)
+        slot["used"] = True
     host = _to_host({"cuts": cuts, "n_cuts": n_cuts})
-    torch.cuda.current_stream(dev).synchronize()
+    cur.wait_stream(s_in)
+    cur.synchronize()
     return host

@@ -158,3 +158,25 @@ def test_edge_cases_and_limits():
         ragged.c99_divisive_cuts(R, plan, [3, 3])
     with pytest.raises(RuntimeError):
         ragged.c99_divisive_cuts(R.cpu(), plan, 3)
+
+
+@pytest.mark.parametrize("local", [False, True])
+def test_c99_cuts_host_pipeline_matches_the_single_pass(local):
+    """The host-buffer C99 operator runs long batches as document chunks with the H2D copy of the next chunk under the
+    kernels of the current one: cuts and counts must equal the one-chunk pass exactly (scalar and per-document
+    min_chunk, empty documents at chunk boundaries)."""
+    from semanticsearch_b200 import ragged
+    rng = np.random.default_rng(33)
+    sizes = [int(x) for x in rng.integers(2, 260, size=70)] + [0, 300, 0, 0, 17, 1]
+    E = torch.from_numpy(rng.standard_normal((sum(sizes), 64)).astype(np.float32)).pin_memory()
+    per_doc = rng.integers(1, 5, size=len(sizes)).astype(np.int32)
+    for mc in (3, per_doc):
+        one = ragged.c99_cuts_host(E, sizes, mc, use_local_rank=local, chunk_bytes=1 << 40)
+        plan = ragged.make_plan(sizes, "cuda")
+        many = ragged.c99_cuts_host(E, sizes, mc, use_local_rank=local, plan=plan, chunk_bytes=1 << 19)
+        assert len(plan.host_chunks[1]) > 5
+        assert torch.equal(one["n_cuts"], many["n_cuts"])
+        off = np.concatenate([[0], np.cumsum(sizes)])
+        for d in range(len(sizes)):
+            k = int(one["n_cuts"][d])
+            assert torch.equal(one["cuts"][off[d]:off[d] + k], many["cuts"][off[d]:off[d] + k]), d
