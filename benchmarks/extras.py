@@ -71,12 +71,14 @@ def cfg1(steps=20, cpu=True):
     hi = torch.empty((100, 10), dtype=torch.int64, pin_memory=True)
 
     def e2e():   # the reference passes the chunk matrix with every call (rank:199,216): chunks and queries both cross the link
-        s, i = similarity.cosine_topk(Cp.cuda(non_blocking=True), Qp.cuda(non_blocking=True), 10)
+        Cd.copy_(Cp, non_blocking=True)          # into the operator's resident buffers: no allocation inside the timed call
+        Qd.copy_(Qp, non_blocking=True)
+        s, i = similarity.cosine_topk(Cd, Qd, 10)
         hs.copy_(s, non_blocking=True)
         hi.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    e2e_s = _wall(e2e, steps, warmup=3)
+    e2e_s = _wall(e2e, steps, warmup=5)
     alg = 4 * (10000 * 384 + 100 * 384) + 100 * 10 * 8
     out = {"workload": "cfg1: 100 queries x 10k chunks x 384 fp32, top-10 cosine (the reference's own scale)",
            "metric": "queries/s", "unit": "queries/s", "value": 100 / (ms * 1e-3), "ms_per_step": ms, "dtype": "f32",
